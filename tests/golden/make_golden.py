@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules on CPU.
+
+Run in the build container only (needs /root/reference, read-only):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference (liruihui/SP-GAN) owns no tests / golden vectors for this path, so the
+fixtures written here are the pins for the oracle (oracle/) and for the CUDA product.
+Weights are synthetic and regenerated from a seed by oracle.spgan_ref.synth_state, so
+only inputs that cannot be regenerated and the reference OUTPUTS are stored.  Large
+gradient tensors are stored as a strided subsample (see `pack`).
+"""
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+REF = os.environ.get("SPGAN_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(1, REF)
+sys.dont_write_bytecode = True
+
+from oracle import spgan_ref as R  # noqa: E402
+
+SUBSAMPLE_ABOVE = 32768
+SUBSAMPLE_STRIDE = 16
+
+
+def pack(t):
+    """fp32 numpy copy; tensors above SUBSAMPLE_ABOVE elements keep every 16th flat element."""
+    a = t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+    if a.dtype == np.float64:
+        a = a.astype(np.float32)
+    if a.size > SUBSAMPLE_ABOVE:
+        a = np.ascontiguousarray(a.reshape(-1)[::SUBSAMPLE_STRIDE])
+    return a
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote %-28s %8.1f KB  keys=%d" % (name + ".npz", os.path.getsize(path) / 1024, len(arrays)))
+
+
+def load_state(module, sd):
+    module.load_state_dict(OrderedDict((k, v.clone()) for k, v in sd.items()), strict=True)
+
+
+def grads_of(module, prefix="grad."):
+    return {prefix + k: pack(p.grad) for k, p in module.named_parameters() if p.grad is not None}
+
+
+def buffers_of(module, prefix="buf."):
+    return {prefix + k: pack(b) for k, b in module.named_buffers()}
+
+
+def sphere(n):
+    ball = np.loadtxt(os.path.join(REF, "template/balls/%d.xyz" % n))[:, :3]
+    return R.normalize_cloud(ball)       # model.py:46-52 restated
+
+
+def main():
+    torch.set_num_threads(8)
+    # importing Generation.modules consumes torch RNG (modules.py:1647-1654): import first, seed after
+    from Generation.Generator import Generator, EdgeBlock, AdaptivePointNorm
+    from Generation.Discriminator import Discriminator
+    from Generation.modules import get_edge_features, edgeConv
+    from Common.gradient_penalty import GradientPenalty
+    torch.Tensor.cuda = lambda self, *a, **k: self          # gradient_penalty.py:24,32 call .cuda()
+
+    # ------------------------------------------------------------------ kNN fixtures
+    ball = sphere(2048)
+    np.save(os.path.join(HERE, "sphere_2048.npy"), ball.astype(np.float32))
+    xs = torch.Tensor(ball)[None].transpose(2, 1).contiguous()          # [1,3,2048]
+    _, idx = get_edge_features(xs, 10, return_idx=True)
+    save("knn_sphere2048", idx=idx.view(1, 2048, 10).numpy().astype(np.int16))
+
+    rng = np.random.default_rng(0)
+    x_c1 = torch.from_numpy(rng.standard_normal((4, 64, 256)).astype(np.float32))
+    ee, idx = get_edge_features(x_c1, 8, return_idx=True)
+    save("knn_config1", x=x_c1.numpy(), idx=idx.view(4, 256, 8).numpy().astype(np.int16),
+         ee_sub=pack(ee))
+
+    rng = np.random.default_rng(1)
+    x_cl = (1.0 + 0.05 * rng.standard_normal((2, 64, 256))).astype(np.float32)   # adversarial: ties
+    _, idx = get_edge_features(torch.from_numpy(x_cl), 10, return_idx=True)
+    save("knn_clustered", x=x_cl, idx=idx.view(2, 256, 10).numpy().astype(np.int16))
+
+    rng = np.random.default_rng(2)
+    for (B, C, N, k) in [(2, 3, 100, 5), (1, 128, 320, 10), (3, 6, 33, 4), (1, 17, 64, 20)]:
+        x = torch.from_numpy(rng.standard_normal((B, C, N)).astype(np.float32))
+        _, idx = get_edge_features(x, k, return_idx=True)
+        save("knn_misc_B%d_C%d_N%d_k%d" % (B, C, N, k), x=x.numpy(),
+             idx=idx.view(B, N, k).numpy().astype(np.int16))
+
+    # ------------------------------------------------------------------ config 1 blocks
+    rng = np.random.default_rng(10)
+    r_out = torch.from_numpy(rng.standard_normal((4, 64, 256)).astype(np.float32))
+    for name, ctor, spec in (("edgeblock", lambda: EdgeBlock(64, 64, 8), R.edge_block_spec("", 64, 64, 8)),
+                             ("edgeconv", lambda: edgeConv(64, 64, 8), R.edge_conv_spec("", 64, 64))):
+        m = ctor()
+        load_state(m, R.synth_state(spec, 11))
+        m.train()
+        x = x_c1.clone().requires_grad_(True)
+        out = m(x)
+        (out * r_out).sum().backward()
+        arrs = {"out_train": out.detach().numpy(), "grad_x": x.grad.numpy(), "r_out": r_out.numpy()}
+        arrs.update(grads_of(m))
+        arrs.update(buffers_of(m))
+        m.eval()
+        with torch.no_grad():
+            arrs["out_eval"] = m(x_c1).numpy()
+        save("config1_" + name, **arrs)
+
+    # ------------------------------------------------------------------ AdaptivePointNorm
+    rng = np.random.default_rng(20)
+    m = AdaptivePointNorm(64, 128)
+    sd = R.synth_state(R._conv("style", (128, 128, 1)), 21)
+    load_state(m, sd)
+    xa = torch.from_numpy(rng.standard_normal((3, 64, 200)).astype(np.float32)).requires_grad_(True)
+    sa = torch.from_numpy(rng.standard_normal((3, 128, 200)).astype(np.float32)).requires_grad_(True)
+    ra = torch.from_numpy(rng.standard_normal((3, 64, 200)).astype(np.float32))
+    out = m(xa, sa)
+    (out * ra).sum().backward()
+    arrs = {"x": xa.detach().numpy(), "style": sa.detach().numpy(), "r": ra.numpy(),
+            "out": out.detach().numpy(), "grad_x": xa.grad.numpy(), "grad_style": sa.grad.numpy()}
+    arrs.update(grads_of(m))
+    save("adain", **arrs)
+
+    # ------------------------------------------------------------------ Discriminator
+    opts = R.default_opts()
+    rng = np.random.default_rng(30)
+    B, N = 4, 256
+    d_sd = R.synth_state(R.discriminator_spec(opts), 31)
+    D = Discriminator(opts)
+    load_state(D, d_sd)
+    D.train()
+    pts = (0.5 * rng.standard_normal((B, N, 3))).astype(np.float32)
+    xd = torch.from_numpy(pts).transpose(2, 1).requires_grad_(True)          # non-contiguous [B,3,N]
+    rd = torch.from_numpy(rng.standard_normal((B, 1)).astype(np.float32))
+    out = D(xd)
+    (out * rd).sum().backward()
+    arrs = {"pts": pts, "r": rd.numpy(), "out_train": out.detach().numpy(), "grad_x": xd.grad.numpy()}
+    arrs.update(grads_of(D))
+    arrs.update(buffers_of(D))
+    D.eval()
+    with torch.no_grad():
+        arrs["out_eval"] = D(torch.from_numpy(pts).transpose(2, 1)).numpy()
+    save("discriminator", **arrs)
+
+    # small_d variant: forward only
+    opts_s = R.default_opts(small_d=True)
+    Ds = Discriminator(opts_s)
+    load_state(Ds, R.synth_state(R.discriminator_spec(opts_s), 32))
+    Ds.train()
+    save("discriminator_small", out_train=Ds(torch.from_numpy(pts).transpose(2, 1)).detach().numpy())
+
+    # ------------------------------------------------------------------ GradientPenalty
+    D = Discriminator(opts)
+    load_state(D, d_sd)
+    D.train()
+    rng = np.random.default_rng(40)
+    real = torch.from_numpy((0.5 * rng.standard_normal((B, 3, N))).astype(np.float32)).requires_grad_(True)
+    fake = torch.from_numpy((0.5 * rng.standard_normal((B + 2, 3, N))).astype(np.float32))   # fake[:B] slice
+    torch.manual_seed(41)
+    alpha = torch.rand(B, 1, 1)
+    torch.manual_seed(41)
+    gp = GradientPenalty(10, gamma=1)(D, real, fake)
+    gp.backward()
+    arrs = {"real": real.detach().numpy(), "fake": fake.numpy(), "alpha": alpha.numpy(),
+            "gp": np.float32(gp.item()), "grad_real": real.grad.numpy()}
+    arrs.update(grads_of(D))
+    arrs.update(buffers_of(D))
+    save("gradient_penalty", **arrs)
+
+    # ------------------------------------------------------------------ Generator
+    ball256 = sphere(256).astype(np.float32)
+    for tag, kw in (("default", {}), ("off_znorm", {"off": True, "z_norm": True}), ("use_head", {"use_head": True})):
+        o = R.default_opts(np=256, **kw)
+        rng = np.random.default_rng(50)
+        Bg = 2
+        g_sd = R.synth_state(R.generator_spec(o), 51)
+        G = Generator(o)
+        load_state(G, g_sd)
+        G.train()
+        xg = torch.from_numpy(np.tile(ball256[None], (Bg, 1, 1)))
+        zg = torch.from_numpy(R.latent_noise(rng, Bg, 256, o.nz))
+        rg = torch.from_numpy(rng.standard_normal((Bg, 3, 256)).astype(np.float32))
+        feats = {}
+        h1 = G.adain1.register_forward_hook(lambda m, i, out: feats.__setitem__("x1", out.detach()))
+        h2 = G.EdgeConv2.register_forward_hook(lambda m, i, out: feats.__setitem__("e2", out.detach()))
+        out = G(xg, zg)
+        h1.remove(); h2.remove()
+        (out * rg).sum().backward()
+        _, idx1 = get_edge_features(xg.transpose(2, 1).contiguous(), o.nk // 2, return_idx=True)
+        arrs = {"z": zg.numpy()[:, :1].copy(), "r": rg.numpy(), "out_train": out.detach().numpy(),
+                "x1": feats["x1"].numpy(), "edgeconv2_out": pack(feats["e2"])}
+        if tag == "default":
+            _, idx2 = get_edge_features(feats["x1"], o.nk // 2, return_idx=True)
+            arrs["idx1"] = idx1.view(Bg, 256, -1).numpy().astype(np.int16)
+            arrs["idx2"] = idx2.view(Bg, 256, -1).numpy().astype(np.int16)
+            arrs.update(grads_of(G))
+            arrs.update(buffers_of(G))
+            G.eval()
+            with torch.no_grad():
+                arrs["out_eval"] = G(xg, zg).numpy()
+                sel = np.zeros(256, np.int64); sel[64:160] = 1
+                z2 = torch.from_numpy(R.latent_noise(rng, Bg, 256, o.nz))
+                arrs["z2"] = z2.numpy()[:, :1].copy()
+                arrs["selection"] = sel
+                arrs["interp_z"] = G.interpolate(xg, zg.clone(), z2, torch.from_numpy(sel), 0.3).numpy()
+                arrs["interp_latent"] = G.interpolate(xg, zg.clone(), z2, torch.from_numpy(sel), 0.3,
+                                                      use_latent=True).numpy()
+        save("generator_" + tag, **arrs)
+
+    # ------------------------------------------------------------------ composed WGAN-GP train step
+    from Common.network_utils import requires_grad
+    o = R.default_opts(np=256)
+    Bt, Nt = 4, 256
+    G, D = Generator(o), Discriminator(o)
+    load_state(G, R.synth_state(R.generator_spec(o), 61))
+    load_state(D, R.synth_state(R.discriminator_spec(o), 62))
+    G.train(); D.train()
+    optG = torch.optim.Adam(filter(lambda p: p.requires_grad, G.parameters()), lr=1e-4, betas=(0.5, 0.99))
+    optD = torch.optim.Adam(filter(lambda p: p.requires_grad, D.parameters()), lr=1e-4, betas=(0.5, 0.99))
+    rng = np.random.default_rng(60)
+    xg = torch.from_numpy(np.tile(ball256[None], (Bt, 1, 1)))
+    gp_fn = GradientPenalty(10, gamma=1)
+    arrs = {}
+    for step in range(2):
+        data = torch.from_numpy(R.synthetic_chairs(rng, Bt, Nt))
+        z_d = torch.from_numpy(R.latent_noise(rng, Bt, Nt, o.nz))
+        z_g = torch.from_numpy(R.latent_noise(rng, Bt, Nt, o.nz))
+        torch.manual_seed(600 + step)
+        alpha = torch.rand(Bt, 1, 1)
+        # ---- model.py:239-260 (+ GP) ----
+        requires_grad(G, False); requires_grad(D, True)
+        optD.zero_grad()
+        real = data.clone().requires_grad_(True)
+        fake = G(xg, z_d)
+        real = real.transpose(2, 1)
+        fake = fake.detach()
+        d_real, d_fake = D(real), D(fake)
+        torch.manual_seed(600 + step)
+        gp = gp_fn(D, real, fake)
+        lossD = (d_fake.mean() - d_real.mean()) + gp
+        lossD.backward()
+        if step == 0:
+            arrs.update(grads_of(D, "s0.gradD."))
+        optD.step()
+        # ---- model.py:264-279 ----
+        requires_grad(G, True); requires_grad(D, False)
+        optG.zero_grad()
+        fake = G(xg, z_g)
+        _ = D(real)
+        lossG = -D(fake).mean()
+        lossG.backward()
+        if step == 0:
+            arrs.update(grads_of(G, "s0.gradG."))
+        optG.step()
+        arrs["s%d.data" % step] = data.numpy()
+        arrs["s%d.z_d" % step] = z_d.numpy()[:, :1].copy()
+        arrs["s%d.z_g" % step] = z_g.numpy()[:, :1].copy()
+        arrs["s%d.alpha" % step] = alpha.numpy()
+        arrs["s%d.loss_d" % step] = np.float32(lossD.item())
+        arrs["s%d.gp" % step] = np.float32(gp.item())
+        arrs["s%d.loss_g" % step] = np.float32(lossG.item())
+        print("train step", step, lossD.item(), gp.item(), lossG.item())
+    arrs.update(buffers_of(G, "end.bufG."))
+    arrs.update(buffers_of(D, "end.bufD."))
+    arrs.update({"end.G." + k: pack(p) for k, p in G.named_parameters()})
+    arrs.update({"end.D." + k: pack(p) for k, p in D.named_parameters()})
+    save("train_step", **arrs)
+    np.save(os.path.join(HERE, "sphere_256.npy"), ball256)
+
+
+if __name__ == "__main__":
+    main()
