@@ -1,0 +1,223 @@
+/*
+ * spgan_b200.h -- C ABI of libspgan_b200.so: the SP-GAN hot path (kNN graph + EdgeConv
+ * generator, PointNet critic, WGAN-GP penalty, optimizer step) as hand-written sm_100a CUDA.
+ *
+ * The reference (liruihui/SP-GAN) has no FFI for this path: it is Python nn.Modules over
+ * torch ops.  Each entry point below therefore cites the reference *operator sequence* it
+ * replaces (file:line relative to the reference tree); the Python host layer in
+ * sp-gan_b200/ mirrors the reference module API on top of these.  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions ("C-ABI"):
+ *   - plain C types only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller allocates every output and workspace; the library never allocates, frees
+ *     or retains a pointer, keeps no mutable global state, and is re-entrant;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*) of the
+ *     caller's current device; no implicit synchronisation; CUDA-graph capturable;
+ *   - return 0 on success, a negative SPGAN_E_* code for argument errors, or a positive
+ *     cudaError_t if the launch failed.  Nothing ever calls exit() or prints.
+ *   - "rows" matrices are row-major fp32 [R, C] with an explicit leading dimension where
+ *     noted; the reference's channel-first tensors are [B, C, N].
+ */
+#ifndef SPGAN_B200_H_
+#define SPGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPGAN_ABI_VERSION 1
+
+#define SPGAN_OK 0
+#define SPGAN_E_BADARG (-1)      /* null pointer / non-positive size / inconsistent shape */
+#define SPGAN_E_UNSUPPORTED (-2) /* valid request outside the implemented envelope (e.g. k+1 > 32) */
+#define SPGAN_E_ALIGN (-3)       /* pointer or leading dimension violates a stated alignment */
+
+typedef void *spgan_stream_t; /* cudaStream_t */
+
+int spgan_abi_version(void);
+/* Static string for a code returned by any entry point (host pointer, never freed). */
+const char *spgan_error_string(int code);
+
+/* ------------------------------------------------------------------ kNN graph + grouping
+ * Replaces Generation/modules.py:695-720 (bmm + sum + add + full sort + slice +
+ * index_select loop + repeat + cat).  Arithmetic of the distance is the reference's CPU
+ * rounding order (see oracle/knn_recipe.c); ties broken by (dist, index). */
+
+/* xs[b,n] = sum_c x[b,c,n]^2, products rounded first, cascade-16 order (modules.py:697).
+ * main_cols < 0 selects the reference default (N/32)*32; columns >= main_cols use the
+ * 4-way interleaved order ATen applies to its vector tail. */
+int spgan_sqnorm(const float *x_bcn, int B, int C, int N, int main_cols, float *xs, spgan_stream_t stream);
+
+/* idx[b,n,r] = rank r+1 of row n of dist (rank 0 dropped), int32 [B,N,k]; 1 <= k <= 31, k < N.
+ * If ee != NULL also writes the grouped edge features ee[B,2C,N,k] (first C channels the
+ * centre point, last C neighbour - centre; modules.py:717-720) in the same kernel. */
+int spgan_knn_group(const float *x_bcn, const float *xs, int B, int C, int N, int k, int32_t *idx,
+                    float *ee, spgan_stream_t stream);
+
+/* Grouping only, for a caller-supplied neighbour list (the `idx=` argument of
+ * get_edge_features, modules.py:683,694).  Indices must lie in [0, N). */
+int spgan_group(const float *x_bcn, const int32_t *idx, int B, int C, int N, int k, float *ee,
+                spgan_stream_t stream);
+
+/* int32 <-> int64 index views (the reference API exposes int64 [B, N*k]). */
+int spgan_idx32_to_idx64(const int32_t *src, int64_t *dst, int64_t n, spgan_stream_t stream);
+int spgan_idx64_to_idx32(const int64_t *src, int32_t *dst, int64_t n, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ layout
+ * [B,C,N] (arbitrary element strides sb, sc, sn) <-> point-major rows [B*N, C].
+ * Replaces the transpose/contiguous calls of Generator.py:167,170 and the strided read of
+ * Discriminator.forward's input (model.py:249). */
+int spgan_bcn_to_rows(const float *src, int64_t sb, int64_t sc, int64_t sn, int B, int C, int N,
+                      float *rows, spgan_stream_t stream);
+int spgan_rows_to_bcn(const float *rows, int B, int C, int N, float *dst, spgan_stream_t stream);
+/* out[r, :] = [a[r, :Ca], b[r, :Cb]]  (torch.cat([x, z], -1), Generator.py:166). sa/sb: row strides
+ * in elements (0 broadcasts one row per segment of seg_rows rows: the tiled latent of model.py:131). */
+int spgan_concat_cols(const float *a, int64_t lda, int Ca, const float *b, int64_t ldb, int64_t b_seg_stride,
+                      int seg_rows, int Cb, int64_t R, float *out, spgan_stream_t stream);
+int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, float *gb, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ dense contraction
+ * C[M,N] = op(A) * op(B) (+ bias[N]) (+ C if accumulate); row-major, fp32 accumulate.
+ * op(A) is A[M,K] (transA=0, lda >= K) or A^T with A stored [K,M] (transA=1, lda >= M);
+ * likewise B stored [K,N] (transB=0) or [N,K] (transB=1).  Replaces every Conv1d(k=1) /
+ * Conv2d(1x1) / Conv2d([1,k]) / Linear of Generator.py:56-71,107-135 and
+ * Discriminator.py:55-94 and their autograd (dgrad: NN, wgrad: TN with split-K).
+ * engine: 0 = fp32 CUDA-core tiles; 1 = tcgen05 tensor cores (bf16x3 split, fp32 accumulate
+ * in TMEM) where the shape allows, else falls back to 0. */
+int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float *A, int64_t lda, const float *B,
+               int64_t ldb, float *C, int64_t ldc, const float *bias, int accumulate, int engine,
+               spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ elementwise
+ * n = element count of flat fp32 tensors unless rows/cols are given. */
+int spgan_fill(float *x, int64_t n, float v, spgan_stream_t stream);
+int spgan_copy(const float *x, float *y, int64_t n, spgan_stream_t stream);
+int spgan_axpby(float a, const float *x, float b, const float *y, float *out, int64_t n, spgan_stream_t stream);
+int spgan_mul(const float *x, const float *y, float *out, int64_t n, spgan_stream_t stream);
+/* LeakyReLU (slope 0 = ReLU): nn.LeakyReLU of Generator.py:59,62,68,111,114,155-156. */
+int spgan_lrelu(const float *x, float slope, float *y, int64_t n, spgan_stream_t stream);
+/* dx = g * (x > 0 ? 1 : slope) */
+int spgan_lrelu_bwd(const float *g, const float *x, float slope, float *dx, int64_t n, spgan_stream_t stream);
+int spgan_tanh(const float *x, float *y, int64_t n, spgan_stream_t stream);             /* Generator.py:135 */
+int spgan_tanh_bwd(const float *g, const float *y, float *dx, int64_t n, spgan_stream_t stream);
+/* out[r,c] = x[r,c] (+|*) v[seg(r), c]; seg(r) = r / seg_rows (seg_rows == R: one row vector). */
+int spgan_add_segvec(const float *x, const float *v, int64_t R, int C, int64_t seg_rows, float *out,
+                     spgan_stream_t stream);
+int spgan_mul_segvec(const float *x, const float *v, int64_t R, int C, int64_t seg_rows, float *out,
+                     spgan_stream_t stream);
+/* out[i] = 1/sqrt(v[i] + eps): eval-mode BatchNorm scale from running_var. */
+int spgan_rsqrt_eps(const float *v, float eps, int64_t n, float *out, spgan_stream_t stream);
+/* out[r,:] = x[r,:] / (||x[r,:]||_2 + eps): the --z_norm latent normalisation (Generator.py:163-164). */
+int spgan_row_l2_normalize(const float *x, int64_t R, int C, float eps, float *out, spgan_stream_t stream);
+/* out[r,c] = v[seg(r), c] */
+int spgan_bcast_segvec(const float *v, int64_t R, int C, int64_t seg_rows, float *out, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ column reductions
+ * Per segment of seg_rows consecutive rows (nseg = R / seg_rows) and per column.
+ * workspace: >= spgan_colreduce_workspace(R, C, seg_rows, nvals) bytes. */
+size_t spgan_colreduce_workspace(int64_t R, int C, int64_t seg_rows, int nvals);
+int spgan_colsum(const float *x, int64_t R, int C, int64_t seg_rows, float *out /*[nseg,C]*/, void *workspace,
+                 spgan_stream_t stream);
+int spgan_coldot(const float *x, const float *y, int64_t R, int C, int64_t seg_rows, float *out, void *workspace,
+                 spgan_stream_t stream);
+/* Batch / instance statistics: mean[nseg,C], rstd = 1/sqrt(biased var + eps), var (biased; may be
+ * NULL).  BatchNorm{1,2}d (one segment) and InstanceNorm1d (segment = cloud) of
+ * Generator.py:29,58,61,67,121,124 and Discriminator.py:57-79. */
+int spgan_colstats(const float *x, int64_t R, int C, int64_t seg_rows, float eps, float *mean, float *rstd,
+                   float *var, void *workspace, spgan_stream_t stream);
+/* y = ((x - mean[s]) * rstd[s]) * gamma + beta, then LeakyReLU(slope) if slope != 1.
+ * gamma/beta: [C] (may be NULL = 1/0). */
+int spgan_norm_apply(const float *x, int64_t R, int C, int64_t seg_rows, const float *mean, const float *rstd,
+                     const float *gamma, const float *beta, float slope, float *y, spgan_stream_t stream);
+/* Running-stat update of nn.BatchNorm (momentum m, unbiased variance): rm = (1-m) rm + m mean,
+ * rv = (1-m) rv + m var * R/(R-1); *count += 1 (int64). */
+int spgan_bn_update_running(const float *mean, const float *var, int C, int64_t R, float momentum, float *rm,
+                            float *rv, int64_t *count, spgan_stream_t stream);
+/* First-order backward of y = act(norm(x)*gamma+beta): given g = dL/dy (post-activation) it
+ * computes sums sg[s,c] = sum g', sgx[s,c] = sum g' * xhat (g' = g masked by the activation
+ * via the saved output y), then dx.  dgamma = sum_s sgx, dbeta = sum_s sg. */
+int spgan_norm_bwd_reduce(const float *g, const float *x, const float *y_act, float slope, int64_t R, int C,
+                          int64_t seg_rows, const float *mean, const float *rstd, float *sg, float *sgx,
+                          void *workspace, spgan_stream_t stream);
+int spgan_norm_bwd_apply(const float *g, const float *x, const float *y_act, float slope, int64_t R, int C,
+                         int64_t seg_rows, const float *mean, const float *rstd, const float *gamma,
+                         const float *sg, const float *sgx, float *dx, spgan_stream_t stream);
+/* Second-order (double) backward of train-mode batch norm, needed by the gradient penalty
+ * (gradient_penalty.py:31-33 with create_graph=True).  Inputs: first-backward operands
+ * (g = dL/dy, x, gamma, mean, rstd) and u = d(loss)/d(dx).  Outputs: gg = d/dg, gx = d/dx,
+ * ggamma[C] = d/dgamma.  Five column sums go through `sums` [5, C] (caller workspace). */
+int spgan_bn_dbl_bwd_reduce(const float *g, const float *u, const float *x, int64_t R, int C, const float *mean,
+                            float *sums /*[5,C]*/, void *workspace, spgan_stream_t stream);
+int spgan_bn_dbl_bwd_apply(const float *g, const float *u, const float *x, int64_t R, int C, const float *mean,
+                           const float *rstd, const float *gamma, const float *sums, float *gg, float *gx,
+                           float *ggamma, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ pooling over points / neighbours
+ * Max over each segment of seg_rows rows (torch.max(x2, 2) Generator.py:183;
+ * adaptive_max_pool1d Discriminator.py:104); arg = row offset inside the segment of the first
+ * maximum (torch semantics). */
+int spgan_segmax(const float *x, int64_t R, int C, int64_t seg_rows, float *out, int32_t *arg,
+                 spgan_stream_t stream);
+/* dx = 0 except dx[s*seg_rows + arg[s,c], c] = g[s,c] */
+int spgan_segmax_scatter(const float *g, const int32_t *arg, int64_t R, int C, int64_t seg_rows, float *dx,
+                         spgan_stream_t stream);
+/* out[s,c] = x[s*seg_rows + arg[s,c], c] */
+int spgan_segmax_gather(const float *x, const int32_t *arg, int64_t R, int C, int64_t seg_rows, float *out,
+                        spgan_stream_t stream);
+/* softmax over the k neighbours of each (point, channel): x, y are [P, k, C] (F.softmax(w, -1),
+ * Generator.py:79) and its backward dx = y * (g - sum_k g*y). */
+int spgan_softmax_k(const float *x, int64_t P, int k, int C, float *y, spgan_stream_t stream);
+int spgan_softmax_k_bwd(const float *g, const float *y, int64_t P, int k, int C, float *dx, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ edge aggregation
+ * out[(p*k + r), :] = (pc ? pc[p,:] : 0) + pn[j,:] - pn[p,:] + bias, j = b(p)*N + idx[p, r]:
+ * the per-edge value of a 1x1 conv applied to [centre, neighbour - centre] expressed through
+ * per-point projections (Generator.py:78,81 and modules.py:793). */
+int spgan_edge_combine(const float *pc, const float *pn, const int32_t *idx, const float *bias, int64_t P, int N,
+                       int k, int C, float *out, spgan_stream_t stream);
+/* Backward: dpc[p] = sum_r g[p,r] (if dpc), dpn[j] += g[p,r], dpn[p] -= sum_r g[p,r] (atomic; dpn is
+ * zeroed by the call). */
+int spgan_edge_combine_bwd(const float *g, const int32_t *idx, int64_t P, int N, int k, int C, float *dpc,
+                           float *dpn, spgan_stream_t stream);
+/* out[p,c] = max_r x[p,r,c] with argmax (torch.max(x, 3), modules.py:794) and its scatter. */
+int spgan_kmax(const float *x, int64_t P, int k, int C, float *out, int32_t *arg, spgan_stream_t stream);
+int spgan_kmax_scatter(const float *g, const int32_t *arg, int64_t P, int k, int C, float *dx, spgan_stream_t stream);
+/* w[o, r, c] <-> w4[o, c, 0, r]: Conv2d(F, F, [1,k]) weight (Generator.py:71) as a [Fout, k*F] matrix. */
+int spgan_permute_ock_to_okc(const float *src, int O, int Cc, int k, float *dst, spgan_stream_t stream);
+int spgan_permute_okc_to_ock(const float *src, int O, int Cc, int k, float *dst, spgan_stream_t stream);
+/* AdaIN apply: out[r,c] = s[r,c] * xhat[r,c] + s[r,C+c], xhat = (x - mean[b,c]) * rstd[b,c]
+ * (Generator.py:38-45) and its backward pieces ds = [g*xhat, g], gxh = g * s[:, :C]. */
+int spgan_adain_apply(const float *x, const float *s, int64_t R, int C, int64_t seg_rows, const float *mean,
+                      const float *rstd, float *out, spgan_stream_t stream);
+int spgan_adain_bwd(const float *g, const float *x, const float *s, int64_t R, int C, int64_t seg_rows,
+                    const float *mean, const float *rstd, float *ds, float *gxh, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ gradient penalty
+ * mix = real + alpha[b] * (fake - real): gradient_penalty.py:26.  real/fake are [B,3,N]-shaped
+ * with element strides; mix is contiguous [B,C,N]. */
+int spgan_gp_interp(const float *real, int64_t rsb, int64_t rsc, int64_t rsn, const float *fake, int64_t fsb,
+                    int64_t fsc, int64_t fsn, const float *alpha, int B, int C, int N, float *mix,
+                    spgan_stream_t stream);
+/* norms[b] = ||g[b,:]||_2; *penalty = lambda * mean_b(((norm - gamma)/gamma)^2): gradient_penalty.py:35. */
+int spgan_gp_penalty(const float *g, int B, int64_t D, float gamma, float lambda, float *norms, float *penalty,
+                     spgan_stream_t stream);
+/* dg[b,:] = gout * lambda * 2 (norm-gamma) / (gamma^2 B norm) * g[b,:] */
+int spgan_gp_penalty_bwd(const float *g, const float *norms, const float *gout, int B, int64_t D, float gamma,
+                         float lambda, float *dg, spgan_stream_t stream);
+/* out[0] = scale * mean(x[0:n]) (+ out[0] if accumulate): the wgan loss means, loss_utils.py:728-730,859-863 */
+int spgan_mean(const float *x, int64_t n, float scale, int accumulate, float *out, spgan_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizer
+ * torch.optim.Adam semantics (model.py:94-97) over one flat parameter buffer: in-place update of
+ * p, m, v from g; step is the 1-based step count. */
+int spgan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, int step, spgan_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPGAN_B200_H_ */

@@ -1,0 +1,16 @@
+"""spgan_b200: the SP-GAN hot path (kNN graph + EdgeConv generator, PointNet critic, WGAN-GP
+penalty and training step) on hand-written sm_100a CUDA behind the reference's module API.
+
+There is no CPU or stock-PyTorch fallback: importing the operator layer loads
+libspgan_b200.so and fails loudly when it is missing.
+"""
+from . import ops  # noqa: F401
+from .edge import get_edge_features, edgeConv, EdgeBlock  # noqa: F401
+from .generator import Generator, AdaptivePointNorm  # noqa: F401
+from .discriminator import Discriminator  # noqa: F401
+from .gradient_penalty import GradientPenalty  # noqa: F401
+from .train_step import WGANGPTrainer, dis_loss_wgan, gen_loss_wgan, requires_grad  # noqa: F401
+
+__all__ = ["ops", "get_edge_features", "edgeConv", "EdgeBlock", "Generator", "AdaptivePointNorm",
+           "Discriminator", "GradientPenalty", "WGANGPTrainer", "dis_loss_wgan", "gen_loss_wgan",
+           "requires_grad"]

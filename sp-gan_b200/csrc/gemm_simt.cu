@@ -1,0 +1,241 @@
+// fp32 CUDA-core GEMM (engine 0 of spgan_gemm): C[M,N] = op(A) op(B) (+bias) (+C).
+// 128 x BN x 16 tiles, 256 threads, 8 x (BN/16) register micro-tiles, register-prefetch double
+// buffering.  transA (wgrad: K = number of points) runs split-K with fp32 atomics.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int APAD = 4;
+
+// Loads 4 consecutive elements along the contiguous axis of an operand tile, guarded.
+// `r` indexes the non-contiguous axis, `c` the contiguous one.
+__device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t ld, int64_t r, int64_t rmax,
+                                        int64_t c, int64_t cmax, bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= rmax) return v;
+    const float* p = base + r * ld + c;
+    if (vec && c + 3 < cmax) {
+        v = __ldg(reinterpret_cast<const float4*>(p));
+    } else {
+        if (c + 0 < cmax) v.x = __ldg(p + 0);
+        if (c + 1 < cmax) v.y = __ldg(p + 1);
+        if (c + 2 < cmax) v.z = __ldg(p + 2);
+        if (c + 3 < cmax) v.w = __ldg(p + 3);
+    }
+    return v;
+}
+
+template <int BN, bool TA, bool TB>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_simt_kernel(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda,
+                 const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
+                 const float* __restrict__ bias, int accumulate, int64_t k_per_split, bool vecA, bool vecB,
+                 bool vecC, bool atomic_out) {
+    constexpr int TN = BN / 16;           // columns per thread (8 or 4)
+    __shared__ __align__(16) float As[2][BK][BM + APAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + APAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int64_t kbeg = (int64_t)blockIdx.z * k_per_split;
+    const int64_t kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+
+    // ---- global -> register staging assignment
+    // A tile: BM x BK.  !TA: A is [M,K], contiguous along k: 4 float4 per row of 16 -> 512 float4, 2 per thread.
+    //                    TA: A is [K,M], contiguous along m: 32 float4 per k-row -> 512 float4, 2 per thread.
+    // B tile: BN x BK.   TB: B is [N,K], contiguous along k;  !TB: B is [K,N], contiguous along n.
+    constexpr int A_V = (BM * BK / 4) / GEMM_THREADS;   // 2
+    constexpr int B_V = (BN * BK / 4) / GEMM_THREADS;   // 2 or 1
+    float4 ra[A_V], rb[B_V];
+
+    auto load_tiles = [&](int64_t k0) {
+#pragma unroll
+        for (int v = 0; v < A_V; ++v) {
+            const int f = tid + v * GEMM_THREADS;
+            if (!TA) {
+                const int row = f >> 2, kq = (f & 3) * 4;
+                ra[v] = load4(A, lda, m0 + row, M, k0 + kq, kend, vecA);
+            } else {
+                const int kr = f >> 5, mq = (f & 31) * 4;
+                ra[v] = load4(A, lda, k0 + kr, kend, m0 + mq, M, vecA);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < B_V; ++v) {
+            const int f = tid + v * GEMM_THREADS;
+            if (TB) {
+                const int row = f >> 2, kq = (f & 3) * 4;
+                rb[v] = load4(B, ldb, n0 + row, N, k0 + kq, kend, vecB);
+            } else {
+                const int kr = f / (BN / 4), nq = (f % (BN / 4)) * 4;
+                rb[v] = load4(B, ldb, k0 + kr, kend, n0 + nq, N, vecB);
+            }
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int v = 0; v < A_V; ++v) {
+            const int f = tid + v * GEMM_THREADS;
+            if (!TA) {
+                const int row = f >> 2, kq = (f & 3) * 4;
+                As[buf][kq + 0][row] = ra[v].x; As[buf][kq + 1][row] = ra[v].y;
+                As[buf][kq + 2][row] = ra[v].z; As[buf][kq + 3][row] = ra[v].w;
+            } else {
+                const int kr = f >> 5, mq = (f & 31) * 4;
+                *reinterpret_cast<float4*>(&As[buf][kr][mq]) = ra[v];
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < B_V; ++v) {
+            const int f = tid + v * GEMM_THREADS;
+            if (TB) {
+                const int row = f >> 2, kq = (f & 3) * 4;
+                Bs[buf][kq + 0][row] = rb[v].x; Bs[buf][kq + 1][row] = rb[v].y;
+                Bs[buf][kq + 2][row] = rb[v].z; Bs[buf][kq + 3][row] = rb[v].w;
+            } else {
+                const int kr = f / (BN / 4), nq = (f % (BN / 4)) * 4;
+                *reinterpret_cast<float4*>(&Bs[buf][kr][nq]) = rb[v];
+            }
+        }
+    };
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    if (kbeg < kend) {
+        load_tiles(kbeg);
+        store_tiles(0);
+        __syncthreads();
+        int buf = 0;
+        for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+            const bool has_next = (k0 + BK) < kend;
+            if (has_next) load_tiles(k0 + BK);
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                float bv[TN];
+                {
+                    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+                    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+                    if (TN == 8) {
+                        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][BN / 2 + tx * 4]);
+                        bv[TN - 4] = b1.x; bv[TN - 3] = b1.y; bv[TN - 2] = b1.z; bv[TN - 1] = b1.w;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            if (has_next) {
+                store_tiles(buf ^ 1);
+                __syncthreads();
+                buf ^= 1;
+            }
+        }
+    }
+
+    // ---- epilogue
+    const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t m = m0 + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int h = 0; h < TN / 4; ++h) {
+            const int n = n0 + ((h == 0) ? tx * 4 : BN / 2 + tx * 4);
+            float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
+            float* cp = C + m * ldc + n;
+            if (add_bias) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) v[j] += __ldg(bias + n + j);
+            }
+            if (atomic_out) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) atomicAdd(cp + j, v[j]);
+            } else if (vecC && n + 3 < N) {
+                if (accumulate) {
+                    const float4 o = *reinterpret_cast<const float4*>(cp);
+                    v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+                }
+                *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < N) cp[j] = accumulate ? cp[j] + v[j] : v[j];
+            }
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN>
+int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st) {
+    const int64_t mt = ceil_div64(M, BM);
+    const int nt = (N + BN - 1) / BN;
+    // split-K when the output grid cannot fill the machine and K is long (wgrad: K = #points)
+    int64_t splits = 1;
+    const int64_t tiles = mt * nt;
+    if (tiles < 2 * kNumSMs && K >= 2048) {
+        splits = (4 * kNumSMs + tiles - 1) / tiles;
+        const int64_t max_splits = K / 512;
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        if (splits > 65535) splits = 65535;
+    }
+    int64_t kps = ceil_div64(ceil_div64(K, splits), BK) * BK;
+    splits = ceil_div64(K, kps);
+    const bool atomic_out = splits > 1;
+    if (atomic_out && !accumulate) {
+        // zero the output rows (ldc may exceed N)
+        cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const bool vecA = (lda % 4 == 0) && aligned16(A);
+    const bool vecB = (ldb % 4 == 0) && aligned16(B);
+    const bool vecC = (ldc % 4 == 0) && aligned16(C);
+    if (mt > 0x7fffffffLL || nt > 65535) return SPGAN_E_UNSUPPORTED;
+    dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)splits);
+#define SPGAN_LAUNCH(TA, TB)                                                                              \
+    gemm_simt_kernel<BN, TA, TB><<<grid, GEMM_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, \
+                                                                 accumulate, kps, vecA, vecB, vecC, atomic_out)
+    if (!transA && !transB) SPGAN_LAUNCH(false, false);
+    else if (!transA && transB) SPGAN_LAUNCH(false, true);
+    else if (transA && !transB) SPGAN_LAUNCH(true, false);
+    else SPGAN_LAUNCH(true, true);
+#undef SPGAN_LAUNCH
+    return spgan_launch_status();
+}
+
+}  // namespace
+
+int spgan_gemm_simt(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                    int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st) {
+    if (N <= 64) return launch_simt<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st);
+    return launch_simt<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st);
+}
+
+
+extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda,
+                          const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate,
+                          int engine, spgan_stream_t stream) {
+    SPGAN_CHECK_ARG(A && B && C && M >= 0 && N >= 1 && K >= 1);
+    SPGAN_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N);
+    if (M == 0) return SPGAN_OK;
+    (void)engine;
+    return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream));
+}

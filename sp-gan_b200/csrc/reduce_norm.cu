@@ -1,0 +1,698 @@
+// Column reductions, batch/instance normalisation (forward, backward, double backward),
+// poolings over points / neighbours, softmax over neighbours, edge aggregation, penalty.
+#include "common.cuh"
+#include <float.h>
+
+namespace {
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------------
+// generic segmented column reduction: partial sums per (segment, row-chunk), then a
+// double-precision finalize.  Block = 32 columns x 8 row lanes.
+// ---------------------------------------------------------------------------------------
+struct ChunkPlan { int64_t nseg; int chunks; int64_t rows_per_chunk; };
+
+inline ChunkPlan plan_chunks(int64_t R, int C, int64_t seg_rows) {
+    ChunkPlan p;
+    p.nseg = R / seg_rows;
+    const int64_t col_blocks = (C + 31) / 32;
+    int64_t want = (8LL * kNumSMs + col_blocks * p.nseg - 1) / (col_blocks * p.nseg);
+    int64_t maxc = (seg_rows + 63) / 64;
+    if (want > maxc) want = maxc;
+    if (want < 1) want = 1;
+    p.rows_per_chunk = ((seg_rows + want - 1) / want + 7) / 8 * 8;
+    p.chunks = (int)((seg_rows + p.rows_per_chunk - 1) / p.rows_per_chunk);
+    return p;
+}
+
+template <int NV, typename Op>
+__global__ void __launch_bounds__(256)
+colreduce_partial_kernel(Op op, int C, int64_t seg_rows, int chunks, int64_t rows_per_chunk,
+                         float* __restrict__ partial) {
+    __shared__ float red[8][NV][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c = blockIdx.x * 32 + tx;
+    const int64_t seg = blockIdx.y / chunks;
+    const int chunk = blockIdx.y % chunks;
+    const int64_t rbeg = seg * seg_rows + (int64_t)chunk * rows_per_chunk;
+    int64_t rend = rbeg + rows_per_chunk;
+    const int64_t seg_end = (seg + 1) * seg_rows;
+    if (rend > seg_end) rend = seg_end;
+    float acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = 0.f;
+    if (c < C) {
+#pragma unroll 4
+        for (int64_t r = rbeg + ty; r < rend; r += 8) op(r, c, seg, acc);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) red[ty][v][tx] = acc[v];
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) s += red[t][v][tx];
+            partial[((int64_t)blockIdx.y * NV + v) * C + c] = s;
+        }
+    }
+}
+
+template <int NV, typename Fin>
+__global__ void colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
+    const int64_t total = nseg * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t seg = i / C;
+        const int c = (int)(i - seg * C);
+        double s[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[v] = 0.0;
+        for (int ch = 0; ch < chunks; ++ch)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) s[v] += (double)partial[(((seg * chunks) + ch) * NV + v) * C + c];
+        fin(seg, c, s);
+    }
+}
+
+template <int NV, typename Op, typename Fin>
+int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStream_t st, Op op, Fin fin) {
+    if (R <= 0) return SPGAN_OK;
+    if (seg_rows < 1 || R % seg_rows != 0 || workspace == nullptr) return SPGAN_E_BADARG;
+    const ChunkPlan p = plan_chunks(R, C, seg_rows);
+    const int64_t gy = p.nseg * p.chunks;
+    if (gy > 65535) return SPGAN_E_UNSUPPORTED;
+    dim3 grid((C + 31) / 32, (unsigned)gy), block(32, 8);
+    float* partial = reinterpret_cast<float*>(workspace);
+    colreduce_partial_kernel<NV><<<grid, block, 0, st>>>(op, C, seg_rows, p.chunks, p.rows_per_chunk, partial);
+    colreduce_final_kernel<NV><<<ew_grid(p.nseg * C, 128), 128, 0, st>>>(partial, C, p.nseg, p.chunks, fin);
+    return spgan_launch_status();
+}
+
+struct SumOp {
+    const float* x; int C;
+    __device__ void operator()(int64_t r, int c, int64_t, float* acc) const { acc[0] += __ldg(x + r * C + c); }
+};
+struct DotOp {
+    const float* x; const float* y; int C;
+    __device__ void operator()(int64_t r, int c, int64_t, float* acc) const {
+        acc[0] += __ldg(x + r * C + c) * __ldg(y + r * C + c);
+    }
+};
+struct Store1Fin {
+    float* out; int C;
+    __device__ void operator()(int64_t seg, int c, const double* s) const { out[seg * C + c] = (float)s[0]; }
+};
+// shifted moments: d = x - x[first row of segment]
+struct StatsOp {
+    const float* x; int C; int64_t seg_rows;
+    __device__ void operator()(int64_t r, int c, int64_t seg, float* acc) const {
+        const float d = __ldg(x + r * C + c) - __ldg(x + seg * seg_rows * C + c);
+        acc[0] += d; acc[1] = fmaf(d, d, acc[1]);
+    }
+};
+struct StatsFin {
+    const float* x; int C; int64_t seg_rows; float eps; float* mean; float* rstd; float* var;
+    __device__ void operator()(int64_t seg, int c, const double* s) const {
+        const double n = (double)seg_rows;
+        const double m1 = s[0] / n;
+        double v = s[1] / n - m1 * m1;
+        if (v < 0.0) v = 0.0;
+        const int64_t o = seg * C + c;
+        mean[o] = (float)((double)x[seg * seg_rows * C + c] + m1);
+        rstd[o] = (float)(1.0 / sqrt(v + (double)eps));
+        if (var) var[o] = (float)v;
+    }
+};
+struct NormBwdOp {
+    const float* g; const float* x; const float* y; float slope; int C; const float* mean; const float* rstd;
+    __device__ void operator()(int64_t r, int c, int64_t seg, float* acc) const {
+        const int64_t i = r * C + c;
+        float gi = __ldg(g + i);
+        if (y != nullptr && !(__ldg(y + i) > 0.f)) gi *= slope;
+        const float xh = (__ldg(x + i) - __ldg(mean + seg * C + c)) * __ldg(rstd + seg * C + c);
+        acc[0] += gi; acc[1] = fmaf(gi, xh, acc[1]);
+    }
+};
+struct Store2Fin {
+    float* a; float* b; int C;
+    __device__ void operator()(int64_t seg, int c, const double* s) const {
+        a[seg * C + c] = (float)s[0]; b[seg * C + c] = (float)s[1];
+    }
+};
+struct DblBwdOp {
+    const float* g; const float* u; const float* x; int C; const float* mean;
+    __device__ void operator()(int64_t r, int c, int64_t, float* acc) const {
+        const int64_t i = r * C + c;
+        const float gi = __ldg(g + i), ui = __ldg(u + i), xm = __ldg(x + i) - __ldg(mean + c);
+        acc[0] += gi; acc[1] += ui; acc[2] = fmaf(gi, xm, acc[2]); acc[3] = fmaf(ui, xm, acc[3]);
+        acc[4] = fmaf(gi, ui, acc[4]);
+    }
+};
+struct Store5Fin {
+    float* out; int C;
+    __device__ void operator()(int64_t, int c, const double* s) const {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) out[v * C + c] = (float)s[v];
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// normalisation maps
+// ---------------------------------------------------------------------------------------
+__global__ void norm_apply_kernel(const float* __restrict__ x, int64_t R, int C, int64_t seg_rows,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                                  float* __restrict__ y) {
+    const int64_t total = R * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const int64_t sc = (r / seg_rows) * C + c;
+        float v = (__ldg(x + i) - __ldg(mean + sc)) * __ldg(rstd + sc);
+        if (gamma) v *= __ldg(gamma + c);
+        if (beta) v += __ldg(beta + c);
+        y[i] = slope == 1.f ? v : lrelu_f(v, slope);
+    }
+}
+
+// dx = gamma * rstd * (g' - sg/n - xhat * sgx/n)
+__global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                      const float* __restrict__ yact, float slope, int64_t R, int C,
+                                      int64_t seg_rows, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                      const float* __restrict__ sg, const float* __restrict__ sgx,
+                                      float* __restrict__ dx) {
+    const int64_t total = R * C;
+    const float inv_n = 1.f / (float)seg_rows;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const int64_t sc = (r / seg_rows) * C + c;
+        float gi = __ldg(g + i);
+        if (yact != nullptr && !(__ldg(yact + i) > 0.f)) gi *= slope;
+        const float rs = __ldg(rstd + sc);
+        const float xh = (__ldg(x + i) - __ldg(mean + sc)) * rs;
+        const float gm = gamma ? __ldg(gamma + c) : 1.f;
+        dx[i] = gm * rs * (gi - __ldg(sg + sc) * inv_n - xh * __ldg(sgx + sc) * inv_n);
+    }
+}
+
+// Double backward of train-mode BN w.r.t. (g, x, gamma) for cotangent u on dx.
+// sums: [Sg, Su, Sgx, Sux, Sgu] with xm = x - mean (not normalised).
+__global__ void bn_dbl_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ u,
+                                        const float* __restrict__ x, int64_t R, int C,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                        const float* __restrict__ gamma, const float* __restrict__ sums,
+                                        float* __restrict__ gg, float* __restrict__ gx) {
+    const int64_t total = R * C;
+    const float inv_n = 1.f / (float)R;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float r1 = __ldg(rstd + c);
+        const float r2 = r1 * r1, r3 = r2 * r1;
+        const float gm = gamma ? __ldg(gamma + c) : 1.f;
+        const float Sg = __ldg(sums + c), Su = __ldg(sums + C + c), Sgx = __ldg(sums + 2 * C + c),
+                    Sux = __ldg(sums + 3 * C + c), Sgu = __ldg(sums + 4 * C + c);
+        const float gi = __ldg(g + i), ui = __ldg(u + i), xm = __ldg(x + i) - __ldg(mean + c);
+        // d/dg: the (linear, self-adjoint) first-backward operator applied to u
+        gg[i] = gm * r1 * (ui - Su * inv_n) - gm * r3 * xm * Sux * inv_n;
+        // d/dx
+        const float all_sub = Su * Sg * inv_n - Sgu + 3.f * r2 * Sgx * Sux * inv_n;
+        const float t0 = xm * r3 * all_sub * inv_n;
+        const float t1 = Sux * r3 * inv_n * (Sg * inv_n - gi);
+        const float t2 = Sgx * r3 * inv_n * (Su * inv_n - ui);
+        gx[i] = gm * (t0 + t1 + t2);
+    }
+}
+__global__ void bn_dbl_bwd_gamma_kernel(int C, int64_t R, const float* __restrict__ rstd,
+                                        const float* __restrict__ sums, float* __restrict__ ggamma) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float inv_n = 1.f / (float)R;
+    const float r1 = rstd[c], r3 = r1 * r1 * r1;
+    const float Sg = sums[c], Su = sums[C + c], Sgx = sums[2 * C + c], Sux = sums[3 * C + c], Sgu = sums[4 * C + c];
+    ggamma[c] = r1 * Sgu - r1 * Su * Sg * inv_n - r3 * Sux * Sgx * inv_n;
+}
+
+__global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, int C,
+                                         float unbias, float momentum, float* __restrict__ rm,
+                                         float* __restrict__ rv, int64_t* count) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && count) *count += 1;
+    if (c >= C) return;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * mean[c];
+    rv[c] = (1.f - momentum) * rv[c] + momentum * (var[c] * unbias);
+}
+
+// ---------------------------------------------------------------------------------------
+// max over the points of a segment (first arg max), scatter / gather by arg
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+segmax_kernel(const float* __restrict__ x, int C, int64_t seg_rows, float* __restrict__ out,
+              int32_t* __restrict__ arg) {
+    __shared__ float bv[8][33];
+    __shared__ int bi[8][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c = blockIdx.x * 32 + tx;
+    const int64_t seg = blockIdx.y;
+    float best = -FLT_MAX;
+    int besti = 0x7fffffff;
+    if (c < C) {
+        const float* base = x + seg * seg_rows * C + c;
+#pragma unroll 4
+        for (int64_t r = ty; r < seg_rows; r += 8) {
+            const float v = __ldg(base + r * C);
+            if (v > best || besti == 0x7fffffff) { best = v; besti = (int)r; }
+        }
+    }
+    bv[ty][tx] = best; bi[ty][tx] = besti;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int t = 1; t < 8; ++t) {
+            const float v = bv[t][tx]; const int j = bi[t][tx];
+            if (j != 0x7fffffff && (besti == 0x7fffffff || v > best || (v == best && j < besti))) { best = v; besti = j; }
+        }
+        out[seg * C + c] = best;
+        if (arg) arg[seg * C + c] = besti;
+    }
+}
+
+__global__ void segmax_scatter_kernel(const float* __restrict__ g, const int32_t* __restrict__ arg, int64_t nseg,
+                                      int C, int64_t seg_rows, float* __restrict__ dx) {
+    const int64_t total = nseg * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t seg = i / C;
+        const int c = (int)(i - seg * C);
+        dx[(seg * seg_rows + arg[i]) * C + c] = g[i];
+    }
+}
+__global__ void segmax_gather_kernel(const float* __restrict__ x, const int32_t* __restrict__ arg, int64_t nseg,
+                                     int C, int64_t seg_rows, float* __restrict__ out) {
+    const int64_t total = nseg * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t seg = i / C;
+        const int c = (int)(i - seg * C);
+        out[i] = x[(seg * seg_rows + arg[i]) * C + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// neighbour-axis ops on [P, k, C]
+// ---------------------------------------------------------------------------------------
+__global__ void softmax_k_kernel(const float* __restrict__ x, int64_t P, int k, int C, float* __restrict__ y) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const float* xp = x + p * k * C + c;
+        float* yp = y + p * k * C + c;
+        float m = -FLT_MAX;
+        for (int r = 0; r < k; ++r) m = fmaxf(m, __ldg(xp + (int64_t)r * C));
+        float s = 0.f;
+        for (int r = 0; r < k; ++r) s += expf(__ldg(xp + (int64_t)r * C) - m);
+        const float inv = 1.f / s;
+        for (int r = 0; r < k; ++r) yp[(int64_t)r * C] = expf(__ldg(xp + (int64_t)r * C) - m) * inv;
+    }
+}
+__global__ void softmax_k_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, int64_t P, int k,
+                                     int C, float* __restrict__ dx) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const int64_t o = p * k * C + c;
+        float s = 0.f;
+        for (int r = 0; r < k; ++r) s = fmaf(__ldg(g + o + (int64_t)r * C), __ldg(y + o + (int64_t)r * C), s);
+        for (int r = 0; r < k; ++r) {
+            const float yy = __ldg(y + o + (int64_t)r * C);
+            dx[o + (int64_t)r * C] = yy * (__ldg(g + o + (int64_t)r * C) - s);
+        }
+    }
+}
+__global__ void kmax_kernel(const float* __restrict__ x, int64_t P, int k, int C, float* __restrict__ out,
+                            int32_t* __restrict__ arg) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const float* xp = x + p * k * C + c;
+        float m = __ldg(xp);
+        int a = 0;
+        for (int r = 1; r < k; ++r) {
+            const float v = __ldg(xp + (int64_t)r * C);
+            if (v > m) { m = v; a = r; }
+        }
+        out[i] = m;
+        if (arg) arg[i] = a;
+    }
+}
+__global__ void kmax_scatter_kernel(const float* __restrict__ g, const int32_t* __restrict__ arg, int64_t P, int k,
+                                    int C, float* __restrict__ dx) {
+    const int64_t total = P * k * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int r = (int)((i / C) % k);
+        const int64_t p = i / ((int64_t)C * k);
+        dx[i] = (arg[p * C + c] == r) ? g[p * C + c] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// edge aggregation through per-point projections
+// ---------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void edge_combine_kernel(const float* __restrict__ pc, const float* __restrict__ pn,
+                                    const int32_t* __restrict__ idx, const float* __restrict__ bias, int64_t P, int N,
+                                    int k, int C, float* __restrict__ out) {
+    constexpr int W = VEC ? 4 : 1;
+    const int Cw = C / W;
+    const int64_t total = P * k * Cw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cw = (int)(i % Cw);
+        const int64_t e = i / Cw;          // edge = p*k + r
+        const int64_t p = e / k;
+        const int64_t j = (p / N) * N + __ldg(idx + e);
+        if (VEC) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(pn + j * C) + cw);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(pn + p * C) + cw);
+            float4 o = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+            if (pc) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(pc + p * C) + cw);
+                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            if (bias) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(bias) + cw);
+                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            reinterpret_cast<float4*>(out)[i] = o;
+        } else {
+            float o = __ldg(pn + j * C + cw) - __ldg(pn + p * C + cw);
+            if (pc) o += __ldg(pc + p * C + cw);
+            if (bias) o += __ldg(bias + cw);
+            out[i] = o;
+        }
+    }
+}
+
+template <bool VEC>
+__global__ void edge_combine_bwd_kernel(const float* __restrict__ g, const int32_t* __restrict__ idx, int64_t P,
+                                        int N, int k, int C, float* __restrict__ dpc, float* __restrict__ dpn) {
+    constexpr int W = VEC ? 4 : 1;
+    const int Cw = C / W;
+    const int64_t total = P * Cw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cw = (int)(i % Cw);
+        const int64_t p = i / Cw;
+        const int64_t base = (p / N) * N;
+        if (VEC) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < k; ++r) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(g + (p * k + r) * C) + cw);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                const int64_t j = base + __ldg(idx + p * k + r);
+                atomicAdd(reinterpret_cast<float4*>(dpn + j * C) + cw, v);
+            }
+            if (dpc) reinterpret_cast<float4*>(dpc + p * C)[cw] = s;
+            atomicAdd(reinterpret_cast<float4*>(dpn + p * C) + cw, make_float4(-s.x, -s.y, -s.z, -s.w));
+        } else {
+            float s = 0.f;
+            for (int r = 0; r < k; ++r) {
+                const float v = __ldg(g + (p * k + r) * C + cw);
+                s += v;
+                const int64_t j = base + __ldg(idx + p * k + r);
+                atomicAdd(dpn + j * C + cw, v);
+            }
+            if (dpc) dpc[p * C + cw] = s;
+            atomicAdd(dpn + p * C + cw, -s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// AdaIN
+// ---------------------------------------------------------------------------------------
+__global__ void adain_apply_kernel(const float* __restrict__ x, const float* __restrict__ s, int64_t R, int C,
+                                   int64_t seg_rows, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   float* __restrict__ out) {
+    const int64_t total = R * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const int64_t sc = (r / seg_rows) * C + c;
+        const float xh = (__ldg(x + i) - __ldg(mean + sc)) * __ldg(rstd + sc);
+        out[i] = fmaf(__ldg(s + r * 2 * C + c), xh, __ldg(s + r * 2 * C + C + c));
+    }
+}
+__global__ void adain_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                 const float* __restrict__ s, int64_t R, int C, int64_t seg_rows,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 float* __restrict__ ds, float* __restrict__ gxh) {
+    const int64_t total = R * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        const int64_t sc = (r / seg_rows) * C + c;
+        const float xh = (__ldg(x + i) - __ldg(mean + sc)) * __ldg(rstd + sc);
+        const float gi = __ldg(g + i);
+        if (ds) { ds[r * 2 * C + c] = gi * xh; ds[r * 2 * C + C + c] = gi; }
+        if (gxh) gxh[i] = gi * __ldg(s + r * 2 * C + c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// gradient penalty reductions
+// ---------------------------------------------------------------------------------------
+__device__ float block_sum(float v) {
+    __shared__ float sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;   // valid in warp 0
+}
+__global__ void gp_norm_kernel(const float* __restrict__ g, int64_t D, float* __restrict__ norms) {
+    const float* gb = g + blockIdx.x * D;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < D; i += blockDim.x) { const float v = __ldg(gb + i); s = fmaf(v, v, s); }
+    s = block_sum(s);
+    if (threadIdx.x == 0) norms[blockIdx.x] = sqrtf(s);
+}
+__global__ void gp_penalty_kernel(const float* __restrict__ norms, int B, float gamma, float lambda,
+                                  float* __restrict__ penalty) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) { const float t = (norms[i] - gamma) / gamma; s = fmaf(t, t, s); }
+    s = block_sum(s);
+    if (threadIdx.x == 0) *penalty = lambda * s / (float)B;
+}
+__global__ void gp_penalty_bwd_kernel(const float* __restrict__ g, const float* __restrict__ norms,
+                                      const float* __restrict__ gout, int B, int64_t D, float gamma, float lambda,
+                                      float* __restrict__ dg) {
+    const int64_t total = (int64_t)B * D;
+    const float go = __ldg(gout);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / D);
+        const float nrm = __ldg(norms + b);
+        const float coef = go * lambda * 2.f * (nrm - gamma) / (gamma * gamma * (float)B * nrm);
+        dg[i] = coef * __ldg(g + i);
+    }
+}
+__global__ void mean_kernel(const float* __restrict__ x, int64_t n, float scale, int accumulate,
+                            float* __restrict__ out) {
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += __ldg(x + i);
+    s = block_sum(s);
+    if (threadIdx.x == 0) {
+        const float v = scale * s / (float)n;
+        *out = accumulate ? *out + v : v;
+    }
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" size_t spgan_colreduce_workspace(int64_t R, int C, int64_t seg_rows, int nvals) {
+    if (R <= 0 || C <= 0 || seg_rows <= 0 || nvals <= 0 || R % seg_rows != 0) return 0;
+    const ChunkPlan p = plan_chunks(R, C, seg_rows);
+    return (size_t)p.nseg * p.chunks * nvals * C * sizeof(float);
+}
+
+extern "C" int spgan_colsum(const float* x, int64_t R, int C, int64_t seg_rows, float* out, void* ws,
+                            spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && out && R >= 0 && C >= 1);
+    return run_colreduce<1>(R, C, seg_rows, ws, as_stream(s), SumOp{x, C}, Store1Fin{out, C});
+}
+extern "C" int spgan_coldot(const float* x, const float* y, int64_t R, int C, int64_t seg_rows, float* out,
+                            void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && y && out && R >= 0 && C >= 1);
+    return run_colreduce<1>(R, C, seg_rows, ws, as_stream(s), DotOp{x, y, C}, Store1Fin{out, C});
+}
+extern "C" int spgan_colstats(const float* x, int64_t R, int C, int64_t seg_rows, float eps, float* mean,
+                              float* rstd, float* var, void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && mean && rstd && R >= 1 && C >= 1);
+    return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), StatsOp{x, C, seg_rows},
+                            StatsFin{x, C, seg_rows, eps, mean, rstd, var});
+}
+extern "C" int spgan_norm_apply(const float* x, int64_t R, int C, int64_t seg_rows, const float* mean,
+                                const float* rstd, const float* gamma, const float* beta, float slope, float* y,
+                                spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && mean && rstd && y && R >= 0 && C >= 1 && seg_rows >= 1);
+    if (R == 0) return SPGAN_OK;
+    norm_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(x, R, C, seg_rows, mean, rstd, gamma, beta,
+                                                                         slope, y);
+    return spgan_launch_status();
+}
+extern "C" int spgan_bn_update_running(const float* mean, const float* var, int C, int64_t R, float momentum,
+                                       float* rm, float* rv, int64_t* count, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(mean && var && rm && rv && C >= 1 && R >= 1);
+    const float unbias = R > 1 ? (float)((double)R / (double)(R - 1)) : 1.f;
+    bn_update_running_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(mean, var, C, unbias, momentum, rm, rv, count);
+    return spgan_launch_status();
+}
+extern "C" int spgan_norm_bwd_reduce(const float* g, const float* x, const float* y_act, float slope, int64_t R,
+                                     int C, int64_t seg_rows, const float* mean, const float* rstd, float* sg,
+                                     float* sgx, void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && R >= 1 && C >= 1);
+    return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), NormBwdOp{g, x, y_act, slope, C, mean, rstd},
+                            Store2Fin{sg, sgx, C});
+}
+extern "C" int spgan_norm_bwd_apply(const float* g, const float* x, const float* y_act, float slope, int64_t R,
+                                    int C, int64_t seg_rows, const float* mean, const float* rstd,
+                                    const float* gamma, const float* sg, const float* sgx, float* dx,
+                                    spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && dx && R >= 1 && C >= 1 && seg_rows >= 1);
+    norm_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, x, y_act, slope, R, C, seg_rows, mean,
+                                                                             rstd, gamma, sg, sgx, dx);
+    return spgan_launch_status();
+}
+extern "C" int spgan_bn_dbl_bwd_reduce(const float* g, const float* u, const float* x, int64_t R, int C,
+                                       const float* mean, float* sums, void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && u && x && mean && sums && R >= 1 && C >= 1);
+    return run_colreduce<5>(R, C, R, ws, as_stream(s), DblBwdOp{g, u, x, C, mean}, Store5Fin{sums, C});
+}
+extern "C" int spgan_bn_dbl_bwd_apply(const float* g, const float* u, const float* x, int64_t R, int C,
+                                      const float* mean, const float* rstd, const float* gamma, const float* sums,
+                                      float* gg, float* gx, float* ggamma, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && u && x && mean && rstd && sums && gg && gx && R >= 1 && C >= 1);
+    bn_dbl_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, u, x, R, C, mean, rstd, gamma, sums,
+                                                                               gg, gx);
+    if (ggamma) bn_dbl_bwd_gamma_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(C, R, rstd, sums, ggamma);
+    return spgan_launch_status();
+}
+
+extern "C" int spgan_segmax(const float* x, int64_t R, int C, int64_t seg_rows, float* out, int32_t* arg,
+                            spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && out && R >= 0 && C >= 1 && seg_rows >= 1 && R % seg_rows == 0);
+    if (R == 0) return SPGAN_OK;
+    const int64_t nseg = R / seg_rows;
+    if (nseg > 65535) return SPGAN_E_UNSUPPORTED;
+    dim3 grid((C + 31) / 32, (unsigned)nseg), block(32, 8);
+    segmax_kernel<<<grid, block, 0, as_stream(s)>>>(x, C, seg_rows, out, arg);
+    return spgan_launch_status();
+}
+extern "C" int spgan_segmax_scatter(const float* g, const int32_t* arg, int64_t R, int C, int64_t seg_rows,
+                                    float* dx, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && arg && dx && R >= 0 && C >= 1 && seg_rows >= 1 && R % seg_rows == 0);
+    if (R == 0) return SPGAN_OK;
+    cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)R * C * sizeof(float), as_stream(s));
+    if (e != cudaSuccess) return (int)e;
+    const int64_t nseg = R / seg_rows;
+    segmax_scatter_kernel<<<ew_grid(nseg * C, 256), 256, 0, as_stream(s)>>>(g, arg, nseg, C, seg_rows, dx);
+    return spgan_launch_status();
+}
+extern "C" int spgan_segmax_gather(const float* x, const int32_t* arg, int64_t R, int C, int64_t seg_rows,
+                                   float* out, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && arg && out && R >= 0 && C >= 1 && seg_rows >= 1 && R % seg_rows == 0);
+    if (R == 0) return SPGAN_OK;
+    const int64_t nseg = R / seg_rows;
+    segmax_gather_kernel<<<ew_grid(nseg * C, 256), 256, 0, as_stream(s)>>>(x, arg, nseg, C, seg_rows, out);
+    return spgan_launch_status();
+}
+extern "C" int spgan_softmax_k(const float* x, int64_t P, int k, int C, float* y, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && y && P >= 0 && k >= 1 && C >= 1);
+    if (P == 0) return SPGAN_OK;
+    softmax_k_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(x, P, k, C, y);
+    return spgan_launch_status();
+}
+extern "C" int spgan_softmax_k_bwd(const float* g, const float* y, int64_t P, int k, int C, float* dx,
+                                   spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && y && dx && P >= 0 && k >= 1 && C >= 1);
+    if (P == 0) return SPGAN_OK;
+    softmax_k_bwd_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(g, y, P, k, C, dx);
+    return spgan_launch_status();
+}
+extern "C" int spgan_kmax(const float* x, int64_t P, int k, int C, float* out, int32_t* arg, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && out && P >= 0 && k >= 1 && C >= 1);
+    if (P == 0) return SPGAN_OK;
+    kmax_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(x, P, k, C, out, arg);
+    return spgan_launch_status();
+}
+extern "C" int spgan_kmax_scatter(const float* g, const int32_t* arg, int64_t P, int k, int C, float* dx,
+                                  spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && arg && dx && P >= 0 && k >= 1 && C >= 1);
+    if (P == 0) return SPGAN_OK;
+    kmax_scatter_kernel<<<ew_grid(P * k * C, 256, 16), 256, 0, as_stream(s)>>>(g, arg, P, k, C, dx);
+    return spgan_launch_status();
+}
+extern "C" int spgan_edge_combine(const float* pc, const float* pn, const int32_t* idx, const float* bias, int64_t P,
+                                  int N, int k, int C, float* out, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(pn && idx && out && P >= 0 && N >= 1 && k >= 1 && C >= 1 && P % N == 0);
+    if (P == 0) return SPGAN_OK;
+    const bool vec = (C % 4 == 0) && al16(pn) && al16(out) && (!pc || al16(pc)) && (!bias || al16(bias));
+    if (vec) edge_combine_kernel<true><<<ew_grid(P * k * (C / 4), 256, 16), 256, 0, as_stream(s)>>>(pc, pn, idx, bias, P, N, k, C, out);
+    else edge_combine_kernel<false><<<ew_grid(P * k * C, 256, 16), 256, 0, as_stream(s)>>>(pc, pn, idx, bias, P, N, k, C, out);
+    return spgan_launch_status();
+}
+extern "C" int spgan_edge_combine_bwd(const float* g, const int32_t* idx, int64_t P, int N, int k, int C, float* dpc,
+                                      float* dpn, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && idx && dpn && P >= 0 && N >= 1 && k >= 1 && C >= 1 && P % N == 0);
+    if (P == 0) return SPGAN_OK;
+    cudaError_t e = cudaMemsetAsync(dpn, 0, (size_t)P * C * sizeof(float), as_stream(s));
+    if (e != cudaSuccess) return (int)e;
+    const bool vec = (C % 4 == 0) && al16(g) && al16(dpn) && (!dpc || al16(dpc));
+    if (vec) edge_combine_bwd_kernel<true><<<ew_grid(P * (C / 4), 256, 16), 256, 0, as_stream(s)>>>(g, idx, P, N, k, C, dpc, dpn);
+    else edge_combine_bwd_kernel<false><<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(g, idx, P, N, k, C, dpc, dpn);
+    return spgan_launch_status();
+}
+extern "C" int spgan_adain_apply(const float* x, const float* sv, int64_t R, int C, int64_t seg_rows,
+                                 const float* mean, const float* rstd, float* out, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && sv && mean && rstd && out && R >= 0 && C >= 1 && seg_rows >= 1);
+    if (R == 0) return SPGAN_OK;
+    adain_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(x, sv, R, C, seg_rows, mean, rstd, out);
+    return spgan_launch_status();
+}
+extern "C" int spgan_adain_bwd(const float* g, const float* x, const float* sv, int64_t R, int C, int64_t seg_rows,
+                               const float* mean, const float* rstd, float* ds, float* gxh, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && x && sv && mean && rstd && R >= 0 && C >= 1 && seg_rows >= 1);
+    if (R == 0) return SPGAN_OK;
+    adain_bwd_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, x, sv, R, C, seg_rows, mean, rstd, ds, gxh);
+    return spgan_launch_status();
+}
+extern "C" int spgan_gp_penalty(const float* g, int B, int64_t D, float gamma, float lambda, float* norms,
+                                float* penalty, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && norms && penalty && B >= 1 && D >= 1);
+    gp_norm_kernel<<<B, 256, 0, as_stream(s)>>>(g, D, norms);
+    gp_penalty_kernel<<<1, 256, 0, as_stream(s)>>>(norms, B, gamma, lambda, penalty);
+    return spgan_launch_status();
+}
+extern "C" int spgan_gp_penalty_bwd(const float* g, const float* norms, const float* gout, int B, int64_t D,
+                                    float gamma, float lambda, float* dg, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && norms && gout && dg && B >= 1 && D >= 1);
+    gp_penalty_bwd_kernel<<<ew_grid((int64_t)B * D, 256), 256, 0, as_stream(s)>>>(g, norms, gout, B, D, gamma, lambda, dg);
+    return spgan_launch_status();
+}
+extern "C" int spgan_mean(const float* x, int64_t n, float scale, int accumulate, float* out, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && out && n >= 1);
+    mean_kernel<<<1, 1024, 0, as_stream(s)>>>(x, n, scale, accumulate, out);
+    return spgan_launch_status();
+}

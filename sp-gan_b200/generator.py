@@ -1,0 +1,180 @@
+"""AdaptivePointNorm and Generator with the reference API (Generation/Generator.py:24-45, 91-261)."""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .edge import EdgeBlock, NEG
+
+NEG_2 = 0.2          # Generator.py:22
+IN_EPS = 1e-5
+
+
+class AdaptivePointNorm(nn.Module):
+    """InstanceNorm1d(input) * gamma + beta with (gamma, beta) = chunk(Conv1d(style)) (Generator.py:24-45)."""
+
+    def __init__(self, in_channel, style_dim, use_eql=False):
+        super().__init__()
+        if use_eql:
+            raise NotImplementedError("--eql (EqualConv1d) is not implemented in spgan_b200 yet")
+        self.in_channel = in_channel
+        self.norm = nn.InstanceNorm1d(in_channel)
+        self.style = nn.Conv1d(style_dim, in_channel * 2, 1)
+        self.style.weight.data.normal_()
+        self.style.bias.data.zero_()
+        self.style.bias.data[:in_channel] = 1
+        self.style.bias.data[in_channel:] = 0
+
+    def forward_rows(self, x_rows, style_rows, N):
+        s = ops.linear(style_rows, self.style.weight, self.style.bias)          # [P, 2C]
+        return ops.AdaIN.apply(x_rows, s, N, self.norm.eps)
+
+    def forward(self, input, style):
+        B, C, N = input.shape
+        out = self.forward_rows(ops.BcnToRows.apply(input), ops.BcnToRows.apply(style), N)
+        return ops.RowsToBcn.apply(out, B, C, N)
+
+
+class Generator(nn.Module):
+    """Sphere-guided generator: forward(x [B,N,3], z [B,N,nz]) -> [B,3,N] (Generator.py:160-198).
+
+    Reads the same opts fields as the reference (np, nk, nz, softmax, off, attn, use_head, eql,
+    z_norm).  Activations stay point-major between the module boundaries; the global feature's
+    512 input channels of tail[0] are folded into a per-cloud bias (results-preserving)."""
+
+    def __init__(self, opts):
+        super().__init__()
+        self.opts = opts
+        self.np = opts.np
+        self.nk = opts.nk // 2
+        self.nz = opts.nz
+        self.off = opts.off
+        self.use_attn = opts.attn
+        self.use_head = opts.use_head
+        if getattr(opts, "eql", False):
+            raise NotImplementedError("--eql (EqualConv1d/EqualLinear) is not implemented in spgan_b200 yet")
+        if self.use_attn:
+            raise NotImplementedError("--attn (N x N Attention(640)) is not implemented in spgan_b200 yet")
+        dim = 128
+        self.head = nn.Sequential(
+            nn.Conv1d(3 + self.nz, dim, 1), nn.LeakyReLU(NEG, inplace=True),
+            nn.Conv1d(dim, dim, 1), nn.LeakyReLU(NEG, inplace=True))
+        self.global_conv = nn.Sequential(
+            nn.Linear(dim, dim), nn.BatchNorm1d(dim), nn.LeakyReLU(NEG, inplace=True),
+            nn.Linear(dim, 512), nn.BatchNorm1d(512), nn.LeakyReLU(NEG, inplace=True))
+        self.tail = nn.Sequential(
+            nn.Conv1d(512 + dim, 256, 1), nn.LeakyReLU(NEG, inplace=True),
+            nn.Conv1d(256, 64, 1), nn.LeakyReLU(NEG, inplace=True),
+            nn.Conv1d(64, 3, 1), nn.Tanh())
+        if self.use_head:
+            self.pc_head = nn.Sequential(
+                nn.Conv1d(3, dim // 2, 1), nn.LeakyReLU(inplace=True),
+                nn.Conv1d(dim // 2, dim, 1), nn.LeakyReLU(inplace=True))
+            self.EdgeConv1 = EdgeBlock(dim, dim, self.nk)
+            self.adain1 = AdaptivePointNorm(dim, dim)
+            self.EdgeConv2 = EdgeBlock(dim, dim, self.nk)
+            self.adain2 = AdaptivePointNorm(dim, dim)
+        else:
+            self.EdgeConv1 = EdgeBlock(3, 64, self.nk)
+            self.adain1 = AdaptivePointNorm(64, dim)
+            self.EdgeConv2 = EdgeBlock(64, dim, self.nk)
+            self.adain2 = AdaptivePointNorm(dim, dim)
+        self.lrelu1 = nn.LeakyReLU(NEG_2)
+        self.lrelu2 = nn.LeakyReLU(NEG_2)
+        self._graph_cache = None          # neighbour list of the static sphere (model.py:231)
+        self.cache_sphere_graph = True
+        self.debug_idx = None             # (idx1, idx2) int32 overrides for parity tests
+
+    # ------------------------------------------------------------------ pieces
+    def _style(self, x_rows, z, B, N):
+        """head(cat([x, z])) (Generator.py:163-168) -> [B*N, 128]."""
+        nz = z.shape[-1]
+        if self.opts.z_norm:
+            z = ops.row_l2_normalize(z if z.is_contiguous() else z.contiguous(), 1e-8)
+        if z.dim() == 3 and z.shape[1] == N and z.stride(1) == 0:
+            zz, bcast = z[:, 0, :], True                 # expanded per-cloud latent: broadcast in-kernel
+        else:
+            zz, bcast = z.reshape(B * N, nz), False
+        s = ops.ConcatCols.apply(x_rows, zz, N, bcast)
+        s = ops.LRelu.apply(ops.linear(s, self.head[0].weight, self.head[0].bias), NEG)
+        return ops.LRelu.apply(ops.linear(s, self.head[2].weight, self.head[2].bias), NEG)
+
+    def _sphere_graph(self, x, pc_rows, B, N):
+        """Neighbour list of EdgeConv1's input.  Without pc_head that input is the sphere itself,
+        which train.py generates once and reuses for every step (model.py:231), so the list is
+        cached on (storage, version, shape) of `x` and recomputed whenever `x` changes."""
+        if self.debug_idx is not None and self.debug_idx[0] is not None:
+            return self.debug_idx[0]
+        knn = lambda: ops.knn_indices(ops.RowsToBcn.apply(pc_rows.detach(), B, pc_rows.shape[1], N), self.nk)
+        if not self.cache_sphere_graph or self.use_head:
+            return knn()
+        key = (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), self.nk, str(x.device))
+        if self._graph_cache is None or self._graph_cache[0] != key:
+            self._graph_cache = (key, knn())
+        return self._graph_cache[1]
+
+    def _body(self, x, x_rows, style, B, N):
+        pc_rows = x_rows
+        if self.use_head:
+            slope = self.pc_head[1].negative_slope
+            pc_rows = ops.LRelu.apply(ops.linear(pc_rows, self.pc_head[0].weight, self.pc_head[0].bias), slope)
+            pc_rows = ops.LRelu.apply(ops.linear(pc_rows, self.pc_head[2].weight, self.pc_head[2].bias), slope)
+        idx1 = self._sphere_graph(x, pc_rows, B, N)
+
+        x1 = self.EdgeConv1.forward_rows(pc_rows, idx1, B, N)
+        x1 = self.adain1.forward_rows(ops.LRelu.apply(x1, NEG_2), style, N)
+
+        if self.debug_idx is not None and self.debug_idx[1] is not None:
+            idx2 = self.debug_idx[1]
+        else:
+            idx2 = ops.knn_indices(ops.RowsToBcn.apply(x1.detach(), B, x1.shape[1], N), self.nk)
+        x2 = self.EdgeConv2.forward_rows(x1, idx2, B, N)
+        x2 = self.adain2.forward_rows(ops.LRelu.apply(x2, NEG_2), style, N)
+        self._last_x1 = x1.detach()
+
+        g = ops.SegMax.apply(x2, N)                                              # [B, 128]
+        gc = self.global_conv
+        g = ops.batch_norm_act(ops.linear(g, gc[0].weight, gc[0].bias), gc[1], NEG)
+        g = ops.batch_norm_act(ops.linear(g, gc[3].weight, gc[3].bias), gc[4], NEG)   # [B, 512]
+
+        # tail[0] over cat(global, x2): the global half is constant per cloud -> per-cloud bias
+        W0 = self.tail[0].weight.view(self.tail[0].weight.shape[0], -1)
+        ng = g.shape[1]
+        gb = ops.linear(g, W0[:, :ng], self.tail[0].bias)                        # [B, 256]
+        t = ops.AddSegVec.apply(ops.linear(x2, W0[:, ng:]), gb, N)
+        t = ops.LRelu.apply(t, NEG)
+        t = ops.LRelu.apply(ops.linear(t, self.tail[2].weight, self.tail[2].bias), NEG)
+        o = ops.Tanh.apply(ops.linear(t, self.tail[4].weight, self.tail[4].bias))
+        if self.off:
+            o = ops.add(pc_rows, o)
+        return ops.RowsToBcn.apply(o, B, 3, N)
+
+    @staticmethod
+    def _rows(x):
+        B, N, C = x.shape
+        x = x if x.is_contiguous() else ops.contiguous(x)
+        return x.view(B * N, C)
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x, z):
+        B, N, _ = x.size()
+        x_rows = self._rows(x)
+        style = self._style(x_rows, z, B, N)
+        return self._body(x, x_rows, style, B, N)
+
+    def interpolate(self, x, z1, z2, selection, alpha, use_latent=False):
+        """Latent / style blending on the points where selection == 1 (Generator.py:200-261).
+        Like the reference, the non-latent branch writes the blend into z1 in place.  The blend
+        itself is index bookkeeping on the caller's tensors and is done with torch indexing."""
+        B, N, _ = x.size()
+        x_rows = self._rows(x)
+        sel = selection == 1
+        if not use_latent:
+            z = z1
+            z[:, sel] = z1[:, sel] * (1 - alpha) + z2[:, sel] * alpha
+            style = self._style(x_rows, z, B, N)
+        else:
+            s1 = self._style(x_rows, z1, B, N).view(B, N, -1)
+            s2 = self._style(x_rows, z2, B, N).view(B, N, -1)
+            s1[:, sel] = s1[:, sel] * (1 - alpha) + s2[:, sel] * alpha
+            style = s1.view(B * N, -1)
+        return self._body(x, x_rows, style, B, N)

@@ -1,0 +1,945 @@
+"""Differentiable operators over libspgan_b200 (torch.autograd.Function wrappers).
+
+PyTorch supplies device memory (the caching allocator), the current CUDA stream and the
+autograd graph; every arithmetic operation below is a kernel of libspgan_b200.so called
+through the C ABI of include/spgan_b200.h.  The set used by the critic is closed under
+differentiation (the backward of each op is built from ops of the same set), which is what
+the gradient penalty's create_graph=True pass needs (Common/gradient_penalty.py:31-33).
+
+Layout: activations are point-major rows [R, C] (R = B*N points or B*N*k edges).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ._lib import lib
+
+_L = None
+
+
+def L():
+    global _L
+    if _L is None:
+        _L = lib()
+    return _L
+
+
+# Set by GradientPenalty while it differentiates w.r.t. the interpolates only
+# (gradient_penalty.py:31-33, only_inputs=True): parameter gradients are not requested there.
+_INPUT_GRAD_ONLY = False
+
+# engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores where supported
+GEMM_ENGINE = 0
+
+
+# Set by GradientPenalty around netD(interpolates): the critic then records the unfused,
+# twice-differentiable operator chain instead of the fused first-order one.
+_TWICE_DIFFERENTIABLE = False
+
+
+class twice_differentiable:
+    def __enter__(self):
+        global _TWICE_DIFFERENTIABLE
+        self.prev = _TWICE_DIFFERENTIABLE
+        _TWICE_DIFFERENTIABLE = True
+
+    def __exit__(self, *a):
+        global _TWICE_DIFFERENTIABLE
+        _TWICE_DIFFERENTIABLE = self.prev
+
+
+def want_twice_differentiable():
+    return _TWICE_DIFFERENTIABLE
+
+
+class input_grad_only:
+    def __enter__(self):
+        global _INPUT_GRAD_ONLY
+        self.prev = _INPUT_GRAD_ONLY
+        _INPUT_GRAD_ONLY = True
+
+    def __exit__(self, *a):
+        global _INPUT_GRAD_ONLY
+        _INPUT_GRAD_ONLY = self.prev
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError("spgan_b200: %s must live on a CUDA device (no CPU fallback exists)" % name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("spgan_b200: %s must be float32, got %s" % (name, t.dtype))
+    return t
+
+
+def _c(t, name="tensor"):
+    """Contiguous fp32 CUDA tensor (copies through our own kernel path only when needed)."""
+    _chk(t, name)
+    return t if t.is_contiguous() else contiguous(t)
+
+
+def contiguous(t):
+    """Materialise a strided <=3-D view with the layout kernel (no torch compute)."""
+    if t.is_contiguous():
+        return t
+    if t.dim() == 2:
+        t3 = t.unsqueeze(0)
+    elif t.dim() == 3:
+        t3 = t
+    else:
+        raise RuntimeError("spgan_b200.contiguous: unsupported rank %d" % t.dim())
+    # treat as [B, C, N] -> rows [B*N, C] of the transposed view, i.e. copy with strides
+    B, C, N = t3.shape
+    out = torch.empty((B, C, N), device=t.device, dtype=t.dtype)
+    # rows_to view: write out[b, c, n] = t3[b, c, n]; use bcn_to_rows on the (b, n, c) permutation
+    tp = t3.permute(0, 2, 1)                          # [B, N, C] view, we want out as [B, C*?]
+    L().bcn_to_rows(tp.data_ptr(), tp.stride(0), tp.stride(1), tp.stride(2), B, N, C, out.data_ptr(), _stream())
+    return out.view(t.shape)
+
+
+def _ws(R, C, seg_rows, nvals, device):
+    n = L().colreduce_workspace(R, C, seg_rows, nvals)
+    return torch.empty((max(n, 4) + 3) // 4, device=device, dtype=torch.float32)
+
+
+def _rows2d(t):
+    if t.dim() != 2:
+        raise RuntimeError("expected a [rows, channels] matrix, got shape %s" % (tuple(t.shape),))
+    return t
+
+
+def _ld(t):
+    """Leading dimension of a 2-D row-major operand view (unit column stride required)."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        return None
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+    return ld if ld >= t.shape[1] else None
+
+
+def _gemm_operand(t):
+    _chk(t)
+    if _ld(t) is None:
+        t = contiguous(t)
+    return t, _ld(t)
+
+
+# =========================================================================================
+# dense contraction
+# =========================================================================================
+def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False):
+    A, lda = _gemm_operand(A)
+    B, ldb = _gemm_operand(B)
+    M = A.shape[1] if ta else A.shape[0]
+    K = A.shape[0] if ta else A.shape[1]
+    Kb = B.shape[1] if tb else B.shape[0]
+    N = B.shape[0] if tb else B.shape[1]
+    if K != Kb:
+        raise RuntimeError("gemm: inner dimensions differ (%d vs %d)" % (K, Kb))
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    if bias is not None:
+        bias = _c(bias)
+    L().gemm(int(ta), int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
+             bias.data_ptr() if bias is not None else None, int(accumulate), GEMM_ENGINE, _stream())
+    return out
+
+
+class Gemm(Function):
+    """C = op(A) @ op(B) + bias.  Closed under differentiation (backward = three Gemm/ColSum)."""
+
+    @staticmethod
+    def forward(ctx, A, B, bias, ta, tb):
+        ctx.ta, ctx.tb = ta, tb
+        ctx.save_for_backward(A, B)
+        ctx.has_bias = bias is not None
+        return gemm_raw(A, B, bias, ta, tb)
+
+    @staticmethod
+    def backward(ctx, g):
+        A, B = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        dA = dB = db = None
+        params_too = not _INPUT_GRAD_ONLY
+        if ctx.needs_input_grad[0]:
+            # C = op(A) op(B):  d op(A) = g op(B)^T
+            dA = Gemm.apply(g, B, None, False, not tb) if not ta else Gemm.apply(B, g, None, tb, True)
+        if ctx.needs_input_grad[1] and params_too:
+            dB = Gemm.apply(A, g, None, not ta, False) if not tb else Gemm.apply(g, A, None, True, ta)
+        if ctx.has_bias and ctx.needs_input_grad[2] and params_too:
+            db = ColSum.apply(g, g.shape[0]).view(-1)
+        return dA, dB, db, None, None
+
+
+def linear(x, weight, bias=None):
+    """x [R, Cin] @ weight[Cout, Cin(,1(,1))]^T + bias -- Conv1d(k=1) / Conv2d(1x1) / Linear."""
+    w = weight.reshape(weight.shape[0], -1) if weight.dim() != 2 else weight
+    return Gemm.apply(x, w, bias, False, True)
+
+
+# =========================================================================================
+# column reductions / broadcasts (mutually adjoint)
+# =========================================================================================
+class ColSum(Function):
+    """[R, C] -> [R/seg_rows, C]"""
+
+    @staticmethod
+    def forward(ctx, x, seg_rows):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        ctx.R, ctx.seg_rows = R, seg_rows
+        out = torch.empty((R // seg_rows, C), device=x.device, dtype=torch.float32)
+        L().colsum(x.data_ptr(), R, C, seg_rows, out.data_ptr(), _ws(R, C, seg_rows, 1, x.device).data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return BcastSeg.apply(g, ctx.R, ctx.seg_rows), None
+
+
+class BcastSeg(Function):
+    """v [nseg, C] -> [R, C] with out[r] = v[r // seg_rows]"""
+
+    @staticmethod
+    def forward(ctx, v, R, seg_rows):
+        v = _c(v)
+        C = v.shape[-1]
+        ctx.seg_rows = seg_rows
+        out = torch.empty((R, C), device=v.device, dtype=torch.float32)
+        L().bcast_segvec(v.data_ptr(), R, C, seg_rows, out.data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ColSum.apply(g, ctx.seg_rows), None, None
+
+
+class AddSegVec(Function):
+    """x [R, C] + v[r // seg_rows] (bias add; per-cloud bias of the folded global feature)."""
+
+    @staticmethod
+    def forward(ctx, x, v, seg_rows):
+        x, v = _c(_rows2d(x)), _c(v)
+        R, C = x.shape
+        ctx.seg_rows, ctx.vshape = seg_rows, v.shape
+        out = torch.empty_like(x)
+        L().add_segvec(x.data_ptr(), v.data_ptr(), R, C, seg_rows, out.data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        dv = None
+        if ctx.needs_input_grad[1] and not _INPUT_GRAD_ONLY:
+            dv = ColSum.apply(g, ctx.seg_rows).view(ctx.vshape)
+        return g, dv, None
+
+
+# =========================================================================================
+# elementwise
+# =========================================================================================
+class Axpby(Function):
+    """a*x + b*y (y may be None)."""
+
+    @staticmethod
+    def forward(ctx, x, y, a, b):
+        x = _c(x)
+        ctx.a, ctx.b = a, b
+        out = torch.empty_like(x)
+        if y is not None:
+            y = _c(y)
+            if y.shape != x.shape:
+                raise RuntimeError("axpby: shape mismatch")
+        L().axpby(a, x.data_ptr(), b, y.data_ptr() if y is not None else None, out.data_ptr(), x.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = Axpby.apply(g, None, ctx.a, 0.0) if ctx.needs_input_grad[0] else None
+        gy = Axpby.apply(g, None, ctx.b, 0.0) if ctx.needs_input_grad[1] else None
+        return gx, gy, None, None
+
+
+def add(x, y):
+    return Axpby.apply(x, y, 1.0, 1.0)
+
+
+def sub(x, y):
+    return Axpby.apply(x, y, 1.0, -1.0)
+
+
+def scale(x, a):
+    return Axpby.apply(x, None, float(a), 0.0)
+
+
+class Mul(Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _c(x), _c(y)
+        ctx.save_for_backward(x, y)
+        out = torch.empty_like(x)
+        L().mul(x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        return (Mul.apply(g, y) if ctx.needs_input_grad[0] else None,
+                Mul.apply(g, x) if ctx.needs_input_grad[1] else None)
+
+
+class LRelu(Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = _c(x)
+        ctx.slope = slope
+        ctx.save_for_backward(x)
+        out = torch.empty_like(x)
+        L().lrelu(x.data_ptr(), slope, out.data_ptr(), x.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return LReluBwd.apply(g, x, ctx.slope), None
+
+
+class LReluBwd(Function):
+    """g * (x > 0 ? 1 : slope): linear in g, piecewise constant in x."""
+
+    @staticmethod
+    def forward(ctx, g, x, slope):
+        g = _c(g)
+        ctx.slope = slope
+        ctx.save_for_backward(x)
+        out = torch.empty_like(g)
+        L().lrelu_bwd(g.data_ptr(), x.data_ptr(), slope, out.data_ptr(), g.numel(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, gg):
+        (x,) = ctx.saved_tensors
+        return LReluBwd.apply(gg, x, ctx.slope), None, None
+
+
+class Tanh(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        out = torch.empty_like(x)
+        L().tanh(x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _c(g)
+        dx = torch.empty_like(g)
+        L().tanh_bwd(g.data_ptr(), y.data_ptr(), dx.data_ptr(), g.numel(), _stream())
+        return dx
+
+
+# =========================================================================================
+# layout
+# =========================================================================================
+class BcnToRows(Function):
+    """[B, C, N] (any strides) -> rows [B*N, C]"""
+
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x)
+        B, C, N = x.shape
+        ctx.shape = (B, C, N)
+        out = torch.empty((B * N, C), device=x.device, dtype=torch.float32)
+        L().bcn_to_rows(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), B, C, N, out.data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return RowsToBcn.apply(g, *ctx.shape)
+
+
+class RowsToBcn(Function):
+    """rows [B*N, C] -> contiguous [B, C, N]"""
+
+    @staticmethod
+    def forward(ctx, rows, B, C, N):
+        rows = _c(rows)
+        out = torch.empty((B, C, N), device=rows.device, dtype=torch.float32)
+        L().rows_to_bcn(rows.data_ptr(), B, C, N, out.data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return BcnToRows.apply(g), None, None, None
+
+
+class ConcatCols(Function):
+    """[a | b] along channels; b may be one row per segment broadcast over seg_rows rows
+    (the tiled latent of model.py:128-131) when b_rows_per_seg == 1."""
+
+    @staticmethod
+    def forward(ctx, a, b, seg_rows, b_broadcast):
+        a, b = _c(_rows2d(a)), _c(_rows2d(b))
+        R, Ca = a.shape
+        Cb = b.shape[1]
+        ctx.dims = (R, Ca, Cb, seg_rows, b_broadcast)
+        out = torch.empty((R, Ca + Cb), device=a.device, dtype=torch.float32)
+        if b_broadcast:
+            L().concat_cols(a.data_ptr(), Ca, Ca, b.data_ptr(), 0, Cb, seg_rows, Cb, R, out.data_ptr(), _stream())
+        else:
+            L().concat_cols(a.data_ptr(), Ca, Ca, b.data_ptr(), Cb, seg_rows * Cb, seg_rows, Cb, R, out.data_ptr(),
+                            _stream())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        R, Ca, Cb, seg_rows, bb = ctx.dims
+        g = _c(g)
+        ga = torch.empty((R, Ca), device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        gb = torch.empty((R, Cb), device=g.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        if ga is not None or gb is not None:
+            L().split_cols_add(g.data_ptr(), R, Ca, Cb, ga.data_ptr() if ga is not None else None,
+                               gb.data_ptr() if gb is not None else None, _stream())
+        if gb is not None and bb:
+            gb = ColSum.apply(gb, seg_rows)
+        return ga, gb, None, None
+
+
+class PermuteOCK(Function):
+    """Conv2d(F, F, [1,k]) weight [O, C, 1, k] -> matrix [O, k*C] (and back in backward)."""
+
+    @staticmethod
+    def forward(ctx, w):
+        w = _c(w)
+        O, Cc, _, k = w.shape
+        ctx.dims = (O, Cc, k)
+        out = torch.empty((O, k * Cc), device=w.device, dtype=torch.float32)
+        L().permute_ock_to_okc(w.data_ptr(), O, Cc, k, out.data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        O, Cc, k = ctx.dims
+        g = _c(g)
+        out = torch.empty((O, Cc, 1, k), device=g.device, dtype=torch.float32)
+        L().permute_okc_to_ock(g.data_ptr(), O, Cc, k, out.data_ptr(), _stream())
+        return out
+
+
+# =========================================================================================
+# normalisation
+# =========================================================================================
+def col_stats(x, seg_rows, eps):
+    x = _c(_rows2d(x))
+    R, C = x.shape
+    nseg = R // seg_rows
+    mean = torch.empty((nseg, C), device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    var = torch.empty_like(mean)
+    L().colstats(x.data_ptr(), R, C, seg_rows, eps, mean.data_ptr(), rstd.data_ptr(), var.data_ptr(),
+                 _ws(R, C, seg_rows, 2, x.device).data_ptr(), _stream())
+    return mean, rstd, var
+
+
+def _norm_bwd(g, x, y_act, slope, seg_rows, mean, rstd, gamma):
+    R, C = x.shape
+    nseg = R // seg_rows
+    sg = torch.empty((nseg, C), device=x.device, dtype=torch.float32)
+    sgx = torch.empty_like(sg)
+    yp = y_act.data_ptr() if y_act is not None else None
+    L().norm_bwd_reduce(g.data_ptr(), x.data_ptr(), yp, slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(),
+                        sg.data_ptr(), sgx.data_ptr(), _ws(R, C, seg_rows, 2, x.device).data_ptr(), _stream())
+    dx = torch.empty_like(x)
+    L().norm_bwd_apply(g.data_ptr(), x.data_ptr(), yp, slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(),
+                       gamma.data_ptr() if gamma is not None else None, sg.data_ptr(), sgx.data_ptr(),
+                       dx.data_ptr(), _stream())
+    return dx, sg, sgx
+
+
+class BatchNormTrain(Function):
+    """Train-mode batch norm over the rows (BatchNorm1d/2d on [B,C,N(,k)]); twice differentiable.
+    Returns (y, batch_mean, biased_batch_var); the last two feed the running-stat update."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        mean, rstd, var = col_stats(x, R, eps)
+        y = torch.empty_like(x)
+        L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                       1.0, y.data_ptr(), _stream())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = BatchNormTrainBwd.apply(gy, x, gamma, mean, rstd)
+        if _INPUT_GRAD_ONLY:
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, None
+
+
+class BatchNormTrainBwd(Function):
+    """(g, x, gamma) -> (dx, dgamma, dbeta) of train-mode BN; its backward is the closed-form
+    double backward (w.r.t. g, x, gamma) for a cotangent on dx."""
+
+    @staticmethod
+    def forward(ctx, g, x, gamma, mean, rstd):
+        g = _c(g)
+        ctx.set_materialize_grads(False)
+        dx, sg, sgx = _norm_bwd(g, x, None, 1.0, x.shape[0], mean, rstd, gamma)
+        ctx.save_for_backward(g, x, gamma, mean, rstd)
+        return dx, sgx.view(-1), sg.view(-1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u, a, c):
+        g, x, gamma, mean, rstd = ctx.saved_tensors
+        if a is not None or c is not None:
+            raise NotImplementedError("double backward through BatchNorm parameter gradients is not needed by "
+                                      "the WGAN-GP step (only_inputs=True) and is not implemented")
+        if u is None:
+            return None, None, None, None, None
+        u = _c(u)
+        R, C = x.shape
+        sums = torch.empty((5, C), device=x.device, dtype=torch.float32)
+        L().bn_dbl_bwd_reduce(g.data_ptr(), u.data_ptr(), x.data_ptr(), R, C, mean.data_ptr(), sums.data_ptr(),
+                              _ws(R, C, R, 5, x.device).data_ptr(), _stream())
+        gg = torch.empty_like(x)
+        gx = torch.empty_like(x)
+        ggamma = torch.empty((C,), device=x.device, dtype=torch.float32)
+        L().bn_dbl_bwd_apply(g.data_ptr(), u.data_ptr(), x.data_ptr(), R, C, mean.data_ptr(), rstd.data_ptr(),
+                             gamma.data_ptr(), sums.data_ptr(), gg.data_ptr(), gx.data_ptr(), ggamma.data_ptr(),
+                             _stream())
+        return gg, gx, ggamma, None, None
+
+
+class BatchNormActTrain(Function):
+    """Fused train-mode BN + LeakyReLU (slope 0 = ReLU); first-order only (generator path)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, slope):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        mean, rstd, var = col_stats(x, R, eps)
+        y = torch.empty_like(x)
+        L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                       slope, y.data_ptr(), _stream())
+        ctx.slope = slope
+        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, _gm, _gv):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        gy = _c(gy)
+        dx, sg, sgx = _norm_bwd(gy, x, y, ctx.slope, x.shape[0], mean, rstd, gamma)
+        return dx, sgx.view(-1), sg.view(-1), None, None
+
+
+class NormAffineEval(Function):
+    """Eval-mode BN (+activation): y = act((x - rm) * rstd * gamma + beta) with frozen statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rm, rstd, slope):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        y = torch.empty_like(x)
+        L().norm_apply(x.data_ptr(), R, C, R, rm.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                       slope, y.data_ptr(), _stream())
+        ctx.slope = slope
+        ctx.save_for_backward(x, y, gamma, rm, rstd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, y, gamma, rm, rstd = ctx.saved_tensors
+        gy = _c(gy)
+        R, C = x.shape
+        # frozen statistics: dx = g' * gamma * rstd, dgamma = sum g' xhat, dbeta = sum g'
+        sg = torch.empty((1, C), device=x.device, dtype=torch.float32)
+        sgx = torch.empty_like(sg)
+        yp = y.data_ptr() if ctx.slope != 1.0 else None
+        L().norm_bwd_reduce(gy.data_ptr(), x.data_ptr(), yp, ctx.slope, R, C, R, rm.data_ptr(), rstd.data_ptr(),
+                            sg.data_ptr(), sgx.data_ptr(), _ws(R, C, R, 2, x.device).data_ptr(), _stream())
+        gmask = gy
+        if ctx.slope != 1.0:
+            gmask = torch.empty_like(gy)
+            L().lrelu_bwd(gy.data_ptr(), y.data_ptr(), ctx.slope, gmask.data_ptr(), gy.numel(), _stream())
+        coef = torch.empty((C,), device=x.device, dtype=torch.float32)
+        L().mul(gamma.data_ptr(), rstd.data_ptr(), coef.data_ptr(), C, _stream())
+        dx = torch.empty_like(x)
+        L().mul_segvec(gmask.data_ptr(), coef.data_ptr(), R, C, R, dx.data_ptr(), _stream())
+        return dx, sgx.view(-1), sg.view(-1), None, None, None
+
+
+class AdaIN(Function):
+    """out = s[:, :C] * InstanceNorm(x) + s[:, C:], statistics per cloud (segment) and channel
+    (Generator.py:38-45); first-order only."""
+
+    @staticmethod
+    def forward(ctx, x, s, seg_rows, eps):
+        x, s = _c(_rows2d(x)), _c(_rows2d(s))
+        R, C = x.shape
+        mean, rstd, _ = col_stats(x, seg_rows, eps)
+        out = torch.empty_like(x)
+        L().adain_apply(x.data_ptr(), s.data_ptr(), R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), out.data_ptr(),
+                        _stream())
+        ctx.seg_rows = seg_rows
+        ctx.save_for_backward(x, s, mean, rstd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, s, mean, rstd = ctx.saved_tensors
+        g = _c(g)
+        R, C = x.shape
+        ds = torch.empty_like(s) if ctx.needs_input_grad[1] else None
+        gxh = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        L().adain_bwd(g.data_ptr(), x.data_ptr(), s.data_ptr(), R, C, ctx.seg_rows, mean.data_ptr(), rstd.data_ptr(),
+                      ds.data_ptr() if ds is not None else None, gxh.data_ptr() if gxh is not None else None, _stream())
+        dx = None
+        if gxh is not None:
+            dx, _, _ = _norm_bwd(gxh, x, None, 1.0, ctx.seg_rows, mean, rstd, None)
+        return dx, ds, None, None
+
+
+def rsqrt_eps(v, eps):
+    v = _c(v)
+    out = torch.empty_like(v)
+    L().rsqrt_eps(v.data_ptr(), float(eps), v.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def row_l2_normalize(x, eps):
+    """x / (||x||_2 + eps) over the last axis; forward only (the latent carries no gradient)."""
+    if x.requires_grad:
+        raise NotImplementedError("z_norm with a latent that requires grad is not supported")
+    x = _c(x)
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    L().row_l2_normalize(x.data_ptr(), x.numel() // C, C, float(eps), out.data_ptr(), _stream())
+    return out
+
+
+def batch_norm_act(y, bn, slope):
+    """nn.BatchNorm{1,2}d (+ LeakyReLU(slope); slope 1 = none) on rows [R, C], honouring bn.training and
+    updating the running statistics like the reference modules do in train mode."""
+    R = y.shape[0]
+    if bn.training or not bn.track_running_stats:
+        if _TWICE_DIFFERENTIABLE:
+            z, mean, var = BatchNormTrain.apply(y, bn.weight, bn.bias, bn.eps)
+            if slope != 1.0:
+                z = LRelu.apply(z, slope)
+        else:
+            z, mean, var = BatchNormActTrain.apply(y, bn.weight, bn.bias, bn.eps, slope)
+        if bn.track_running_stats and bn.training:
+            bn_update_running(mean, var, R, bn)
+        return z
+    return NormAffineEval.apply(y, bn.weight, bn.bias, bn.running_mean, rsqrt_eps(bn.running_var, bn.eps), slope)
+
+
+def bn_update_running(mean, var, R, bn):
+    """Side effect of a train-mode forward on nn.BatchNorm buffers (momentum, unbiased var, count)."""
+    m = bn.momentum if bn.momentum is not None else 0.1
+    L().bn_update_running(mean.data_ptr(), var.data_ptr(), mean.numel(), R, float(m), bn.running_mean.data_ptr(),
+                          bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _stream())
+
+
+# =========================================================================================
+# pooling over points / neighbours
+# =========================================================================================
+class SegMax(Function):
+    """max over each segment of seg_rows rows -> ([nseg, C]); gradient to the first arg max."""
+
+    @staticmethod
+    def forward(ctx, x, seg_rows):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        out = torch.empty((R // seg_rows, C), device=x.device, dtype=torch.float32)
+        arg = torch.empty((R // seg_rows, C), device=x.device, dtype=torch.int32)
+        L().segmax(x.data_ptr(), R, C, seg_rows, out.data_ptr(), arg.data_ptr(), _stream())
+        ctx.dims = (R, seg_rows)
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        return SegMaxScatter.apply(g, arg, *ctx.dims), None
+
+
+class SegMaxScatter(Function):
+    @staticmethod
+    def forward(ctx, g, arg, R, seg_rows):
+        g = _c(g)
+        C = g.shape[1]
+        dx = torch.empty((R, C), device=g.device, dtype=torch.float32)
+        L().segmax_scatter(g.data_ptr(), arg.data_ptr(), R, C, seg_rows, dx.data_ptr(), _stream())
+        ctx.dims = (R, seg_rows)
+        ctx.save_for_backward(arg)
+        return dx
+
+    @staticmethod
+    def backward(ctx, gg):
+        (arg,) = ctx.saved_tensors
+        return SegMaxGather.apply(gg, arg, *ctx.dims), None, None, None
+
+
+class SegMaxGather(Function):
+    @staticmethod
+    def forward(ctx, x, arg, R, seg_rows):
+        x = _c(x)
+        C = x.shape[1]
+        out = torch.empty((R // seg_rows, C), device=x.device, dtype=torch.float32)
+        L().segmax_gather(x.data_ptr(), arg.data_ptr(), R, C, seg_rows, out.data_ptr(), _stream())
+        ctx.dims = (R, seg_rows)
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        return SegMaxScatter.apply(g, arg, *ctx.dims), None, None, None
+
+
+class SoftmaxK(Function):
+    """softmax over the k neighbours; x is [P*k, C] edge-major (F.softmax(w, -1), Generator.py:79)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        x = _c(_rows2d(x))
+        E, C = x.shape
+        y = torch.empty_like(x)
+        L().softmax_k(x.data_ptr(), E // k, k, C, y.data_ptr(), _stream())
+        ctx.k = k
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _c(g)
+        E, C = y.shape
+        dx = torch.empty_like(y)
+        L().softmax_k_bwd(g.data_ptr(), y.data_ptr(), E // ctx.k, ctx.k, C, dx.data_ptr(), _stream())
+        return dx, None
+
+
+class KMax(Function):
+    """max over the k neighbours: [P*k, C] -> [P, C] (torch.max(x, 3), modules.py:794)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        x = _c(_rows2d(x))
+        E, C = x.shape
+        P = E // k
+        out = torch.empty((P, C), device=x.device, dtype=torch.float32)
+        arg = torch.empty((P, C), device=x.device, dtype=torch.int32)
+        L().kmax(x.data_ptr(), P, k, C, out.data_ptr(), arg.data_ptr(), _stream())
+        ctx.k = k
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        g = _c(g)
+        P, C = g.shape
+        dx = torch.empty((P * ctx.k, C), device=g.device, dtype=torch.float32)
+        L().kmax_scatter(g.data_ptr(), arg.data_ptr(), P, ctx.k, C, dx.data_ptr(), _stream())
+        return dx, None
+
+
+class EdgeCombine(Function):
+    """out[p*k+r] = pc[p] + pn[nbr(p,r)] - pn[p] + bias: a 1x1 conv over [centre, nbr - centre]
+    expressed through per-point projections (pc may be None for a conv on the difference half)."""
+
+    @staticmethod
+    def forward(ctx, pc, pn, bias, idx, N, k):
+        pn = _c(_rows2d(pn))
+        P, C = pn.shape
+        if pc is not None:
+            pc = _c(pc)
+        if bias is not None:
+            bias = _c(bias)
+        out = torch.empty((P * k, C), device=pn.device, dtype=torch.float32)
+        L().edge_combine(pc.data_ptr() if pc is not None else None, pn.data_ptr(), idx.data_ptr(),
+                         bias.data_ptr() if bias is not None else None, P, N, k, C, out.data_ptr(), _stream())
+        ctx.dims = (P, C, N, k)
+        ctx.has = (pc is not None, bias is not None)
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        P, C, N, k = ctx.dims
+        g = _c(g)
+        has_pc, has_bias = ctx.has
+        dpc = torch.empty((P, C), device=g.device, dtype=torch.float32) if (has_pc and ctx.needs_input_grad[0]) else None
+        dpn = torch.empty((P, C), device=g.device, dtype=torch.float32)
+        L().edge_combine_bwd(g.data_ptr(), idx.data_ptr(), P, N, k, C, dpc.data_ptr() if dpc is not None else None,
+                             dpn.data_ptr(), _stream())
+        db = None
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ColSum.apply(g, g.shape[0]).view(-1)
+        return dpc, dpn, db, None, None, None
+
+
+# =========================================================================================
+# kNN graph (no gradient: indices)
+# =========================================================================================
+def knn_indices(x_bcn, k, want_ee=False, main_cols=-1):
+    """x [B, C, N] contiguous fp32 -> idx int32 [B, N, k] (ranks 1..k of the reference's sorted
+    distance rows, modules.py:695-704); optionally the grouped edge features [B, 2C, N, k]."""
+    x = _c(x_bcn.detach())
+    B, C, N = x.shape
+    xs = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    L().sqnorm(x.data_ptr(), B, C, N, main_cols, xs.data_ptr(), _stream())
+    idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
+    ee = torch.empty((B, 2 * C, N, k), device=x.device, dtype=torch.float32) if want_ee else None
+    L().knn_group(x.data_ptr(), xs.data_ptr(), B, C, N, k, idx.data_ptr(),
+                  ee.data_ptr() if ee is not None else None, _stream())
+    return (idx, ee) if want_ee else idx
+
+
+def idx_to_int64(idx32):
+    out = torch.empty(idx32.shape, device=idx32.device, dtype=torch.int64)
+    L().idx32_to_idx64(idx32.data_ptr(), out.data_ptr(), idx32.numel(), _stream())
+    return out
+
+
+def idx_to_int32(idx64):
+    idx64 = idx64.contiguous()
+    out = torch.empty(idx64.shape, device=idx64.device, dtype=torch.int32)
+    L().idx64_to_idx32(idx64.data_ptr(), out.data_ptr(), idx64.numel(), _stream())
+    return out
+
+
+class Group(Function):
+    """ee[B, 2C, N, k] = cat(centre, neighbour - centre) for a given neighbour list
+    (modules.py:706-720); backward scatters with the edge-aggregation kernel."""
+
+    @staticmethod
+    def forward(ctx, x, idx32, k):
+        x = _c(x)
+        B, C, N = x.shape
+        ee = torch.empty((B, 2 * C, N, k), device=x.device, dtype=torch.float32)
+        L().group(x.data_ptr(), idx32.data_ptr(), B, C, N, k, ee.data_ptr(), _stream())
+        ctx.dims = (B, C, N, k)
+        ctx.save_for_backward(idx32)
+        return ee
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (idx32,) = ctx.saved_tensors
+        B, C, N, k = ctx.dims
+        g = _c(g)
+        # d x[b,c,i] = sum_r g_ctr[b,c,i,r] - sum_r g_dif[b,c,i,r] + sum_{(p,r): nbr(p,r)=i} g_dif[b,c,p,r]
+        # route through edge-major rows: [B, 2C, N*k] -> rows [B*N*k, 2C]
+        rows = torch.empty((B * N * k, 2 * C), device=g.device, dtype=torch.float32)
+        g3 = g.view(B, 2 * C, N * k)
+        L().bcn_to_rows(g3.data_ptr(), g3.stride(0), g3.stride(1), g3.stride(2), B, 2 * C, N * k, rows.data_ptr(),
+                        _stream())
+        g_ctr = contiguous(rows[:, :C])
+        g_dif = contiguous(rows[:, C:])
+        dpc = torch.empty((B * N, C), device=g.device, dtype=torch.float32)
+        dpn = torch.empty((B * N, C), device=g.device, dtype=torch.float32)
+        junk = torch.empty((B * N, C), device=g.device, dtype=torch.float32)
+        L().edge_combine_bwd(g_dif.data_ptr(), idx32.data_ptr(), B * N, N, k, C, None, dpn.data_ptr(), _stream())
+        L().colsum(g_ctr.data_ptr(), B * N * k, C, k, dpc.data_ptr(),
+                   _ws(B * N * k, C, k, 1, g.device).data_ptr(), _stream())
+        L().axpby(1.0, dpc.data_ptr(), 1.0, dpn.data_ptr(), junk.data_ptr(), dpc.numel(), _stream())
+        dx = torch.empty((B, C, N), device=g.device, dtype=torch.float32)
+        L().rows_to_bcn(junk.data_ptr(), B, C, N, dx.data_ptr(), _stream())
+        return dx, None, None
+
+
+# =========================================================================================
+# losses / penalty
+# =========================================================================================
+class MeanScale(Function):
+    """scale * mean(x) as a 0-d tensor (wgan loss terms, loss_utils.py:728-730, 859-863)."""
+
+    @staticmethod
+    def forward(ctx, x, scale_):
+        x = _c(x)
+        ctx.n, ctx.scale, ctx.shape = x.numel(), scale_, x.shape
+        out = torch.empty((), device=x.device, dtype=torch.float32)
+        L().mean(x.data_ptr(), x.numel(), scale_, 0, out.data_ptr(), _stream())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = _c(g)
+        coef = torch.empty((1,), device=g.device, dtype=torch.float32)
+        L().axpby(ctx.scale / ctx.n, g.data_ptr(), 0.0, None, coef.data_ptr(), 1, _stream())
+        out = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        L().bcast_segvec(coef.data_ptr(), ctx.n, 1, ctx.n, out.data_ptr(), _stream())
+        return out, None
+
+
+class GradPenalty(Function):
+    """lambda * mean_b(((||g_b||_2 - gamma) / gamma)^2) over g [B, D] (gradient_penalty.py:35)."""
+
+    @staticmethod
+    def forward(ctx, g, gamma, lam):
+        g = _c(g)
+        B, D = g.shape
+        norms = torch.empty((B,), device=g.device, dtype=torch.float32)
+        out = torch.empty((), device=g.device, dtype=torch.float32)
+        L().gp_penalty(g.data_ptr(), B, D, gamma, lam, norms.data_ptr(), out.data_ptr(), _stream())
+        ctx.consts = (gamma, lam)
+        ctx.save_for_backward(g, norms)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        g, norms = ctx.saved_tensors
+        gamma, lam = ctx.consts
+        gout = _c(gout)
+        B, D = g.shape
+        dg = torch.empty_like(g)
+        L().gp_penalty_bwd(g.data_ptr(), norms.data_ptr(), gout.data_ptr(), B, D, gamma, lam, dg.data_ptr(), _stream())
+        return dg, None, None
+
+
+def gp_interpolate(real, fake, alpha):
+    """mix = real + alpha * (fake - real); real/fake [B,C,N] with any strides, alpha [B] (gradient_penalty.py:26)."""
+    _chk(real), _chk(fake)
+    alpha = _c(alpha.reshape(-1))
+    B, C, N = real.shape
+    mix = torch.empty((B, C, N), device=real.device, dtype=torch.float32)
+    L().gp_interp(real.data_ptr(), real.stride(0), real.stride(1), real.stride(2), fake.data_ptr(), fake.stride(0),
+                  fake.stride(1), fake.stride(2), alpha.data_ptr(), B, C, N, mix.data_ptr(), _stream())
+    return mix
+
+
+def fill_(t, v):
+    L().fill(t.data_ptr(), t.numel(), float(v), _stream())
+    return t
+
+
+def full(shape, v, device):
+    return fill_(torch.empty(shape, device=device, dtype=torch.float32), v)
