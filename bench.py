@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- point-clouds/sec of the full G+D WGAN-GP training step at N=2048, B=64 per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+One "step" = one iteration of Generation/model.py:239-279 with gan='wgan' plus
+GradientPenalty(10) (BASELINE.json configs[2]: "Full G+D WGAN-GP training step, Chair synthetic,
+N=2048 B=64").  Rank 0 prints ONE JSON line.  `value` is timed with the inputs already resident in
+HBM; `e2e` goes through the same public API with pinned-host inputs copied every step and the losses
+read back.  Batches shard across ranks (weak scaling, 64 clouds per GPU, BN statistics per replica as
+in the reference's DataParallel) with one NCCL all-reduce of a flat gradient buffer per phase.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "point-clouds/sec per G+D WGAN-GP step at N=2048 B=64"
+UNIT = "clouds/s"
+N_POINTS, BATCH, NZ = 2048, 64, 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="spgan_b200", choices=["spgan_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port timing (N=1 only runs it)")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="clouds in the bounded CPU sample")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--engine", type=int, default=None, help="spgan_gemm engine (0 fp32 CUDA cores, 1 tcgen05)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------
+def cpu_step_time(batch, points, steps, warmup, seed=123):
+    import numpy as np
+    import torch
+    from oracle import spgan_ref as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    o = R.default_opts(np=points)
+    st = R.TrainState(R.synth_state(R.generator_spec(o), 1), R.synth_state(R.discriminator_spec(o), 2), o)
+    rng = np.random.default_rng(seed)
+    from spgan_b200.synthetic import sphere_template
+    ball, _ = sphere_template(points)
+    x = torch.from_numpy(np.tile(ball[None], (batch, 1, 1)))
+    times = []
+    for it in range(warmup + steps):
+        real = torch.from_numpy(R.synthetic_chairs(rng, batch, points)).transpose(2, 1)
+        z_d = torch.from_numpy(R.latent_noise(rng, batch, points, o.nz))
+        z_g = torch.from_numpy(R.latent_noise(rng, batch, points, o.nz))
+        alpha = torch.rand(batch, 1, 1)
+        t0 = time.perf_counter()
+        R.wgan_gp_train_step(st, x, z_d, z_g, real, alpha)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: pick the per-step batch so that the whole run stays within a few minutes
+    t_probe, cores = cpu_step_time(2, args.points, 1, 0)
+    budget = 150.0
+    b = int(budget / max(1e-3, (args.steps + args.warmup) * t_probe / 2.0))
+    b = max(2, min(args.batch, b))
+    t, cores = cpu_step_time(b, args.points, args.steps, args.warmup)
+    value = b / t
+    sample = "each step = one full WGAN-GP step on %d of the %d clouds (N=%d)" % (b, args.batch, args.points)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: full G+D WGAN-GP step, Chair synthetic, N=%d B=%d" % (args.points, args.batch),
+                       "parallelism": "cpu", "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def gemm_flops(args_):
+    return 2.0 * args_[2] * args_[3] * args_[4]
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import spgan_b200 as pkg
+    from spgan_b200 import synthetic
+    from spgan_b200._lib import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- spgan_b200 has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.engine is not None:
+        pkg.ops.GEMM_ENGINE = args.engine
+    B, N = args.batch, args.points
+
+    # ---- model: same random-init architecture on every rank (seed 123 as Generation/model.py:38-41)
+    torch.manual_seed(123)
+    opts = type("Opts", (), dict(np=N, nk=20, nz=NZ, softmax=True, off=False, attn=False, use_head=False,
+                                 eql=False, z_norm=False, small_d=False))()
+    G, D = pkg.Generator(opts).to(dev).train(), pkg.Discriminator(opts).to(dev).train()
+    trainer = pkg.WGANGPTrainer(G, D, lambda_gp=10.0, gamma=1.0)
+
+    # ---- synthetic inputs: different clouds / latents per rank, pinned on the host
+    rng = np.random.default_rng(123 + rank)
+    ball, ball_src = synthetic.sphere_template(N)
+    x = torch.from_numpy(np.tile(ball[None], (B, 1, 1))).to(dev)           # constant of training (model.py:231)
+    n_pool = 4
+    host = []
+    for _ in range(n_pool):
+        host.append(dict(real=torch.from_numpy(synthetic.synthetic_chairs(rng, B, N)).pin_memory(),
+                         z_d=torch.from_numpy(synthetic.latent_vectors(rng, B, NZ)).pin_memory(),
+                         z_g=torch.from_numpy(synthetic.latent_vectors(rng, B, NZ)).pin_memory(),
+                         alpha=torch.rand(B, 1, 1).pin_memory()))
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+
+    def step_on(d):
+        real = d["real"].transpose(2, 1)                                   # strided view, as model.py:249
+        return trainer.step(x, d["z_d"].expand(B, N, NZ), d["z_g"].expand(B, N, NZ), real, alpha=d["alpha"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    L = lib()
+    for i in range(args.warmup):
+        step_on(resident[i % n_pool])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = L.launches
+    ms = timed(lambda i: step_on(resident[i % n_pool]), args.steps)
+    launches = L.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host -> device every step, losses read back every step
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    losses = []
+
+    def e2e_step(i):
+        d = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_pool].items()}
+        out = step_on(d)
+        losses.append([float(t) for t in out])                              # D2H of the three step results
+
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps}
+
+    # ---- per-kernel device times of one more step (CUDA events around every C-ABI launch)
+    roofline, kernel_share = None, None
+    if rank == 0:
+        L.profile = []
+        step_on(resident[0])
+        torch.cuda.synchronize()
+        prof, L.profile = L.profile, None
+        agg = {}
+        for name, ia, s, e in prof:
+            t = s.elapsed_time(e)
+            a = agg.setdefault(name, [0.0, 0, 0.0])
+            a[0] += t
+            a[1] += 1
+            if name == "spgan_gemm":
+                a[2] += gemm_flops(ia)
+        total = sum(a[0] for a in agg.values())
+        kernel_share = {k[len("spgan_"):]: round(a[0] / total, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        g = agg.get("spgan_gemm")
+        if g:
+            peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            ach = g[2] / (g[0] / 1e3) / 1e12
+            roofline = {"kernel": "spgan_gemm (%s)" % ("tcgen05" if pkg.ops.GEMM_ENGINE == 1 else "fp32 CUDA cores"),
+                        "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": None, "launches_per_step": g[1], "avg_launch_ms": g[0] / g[1],
+                        "share_of_step": g[0] / total,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_cpu, cores = cpu_step_time(args.cpu_batch, N, 1, 0)
+        cpu_baseline = {"value": args.cpu_batch / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "1 full WGAN-GP step on %d of the %d clouds (N=%d), oracle port of the reference's "
+                                  "torch CPU path" % (args.cpu_batch, B, N), "ms_per_step": 1e3 * t_cpu}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[2]: full G+D WGAN-GP step, Chair synthetic, N=%d B=%d per GPU" % (N, B),
+                           "global_batch": world * B, "points": N, "k": 10, "parallelism": "dp%d" % world,
+                           "sphere": ball_src, "gemm_engine": pkg.ops.GEMM_ENGINE,
+                           "l2": "no flush needed: per-step working set (activations) is several GB >> 126 MB L2"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "kernel_share": kernel_share, "cpu_baseline": cpu_baseline,
+                "last_losses": losses[-1] if losses else None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -332,8 +332,8 @@ class TrainState:
 
     def __init__(self, g_state, d_state, opts, lr_g=1e-4, lr_d=1e-4, betas=(0.5, 0.99)):
         self.opts = opts
-        self.g = OrderedDict((k, v.clone()) for k, v in g_state.items())
-        self.d = OrderedDict((k, v.clone()) for k, v in d_state.items())
+        self.g = OrderedDict((k, v.detach().clone()) for k, v in g_state.items())
+        self.d = OrderedDict((k, v.detach().clone()) for k, v in d_state.items())
         self.g_params = [k for k, v in self.g.items() if v.is_floating_point() and "running_" not in k]
         self.d_params = [k for k, v in self.d.items() if v.is_floating_point() and "running_" not in k]
         self.opt_g = torch.optim.Adam([self.g[k] for k in self.g_params], lr=lr_g, betas=betas)

@@ -47,8 +47,19 @@ class SpganError(RuntimeError):
     pass
 
 
+# kernel launches behind one C-ABI call (1 unless listed)
+_LAUNCHES = {"spgan_colsum": 2, "spgan_coldot": 2, "spgan_colstats": 2, "spgan_norm_bwd_reduce": 2,
+             "spgan_bn_dbl_bwd_reduce": 2, "spgan_bn_dbl_bwd_apply": 2, "spgan_gp_penalty": 2}
+
+
 class _Library:
+    """Counters: `launches` = kernels launched so far through this binding; `profile` (None or list):
+    when a list, every call is bracketed by CUDA events on the current torch stream and appended as
+    (name, int args, start_event, end_event) -- used by bench.py for per-kernel device times."""
+
     def __init__(self):
+        self.launches = 0
+        self.profile = None
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 "libspgan_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; "
@@ -68,11 +79,21 @@ class _Library:
 
     def _checked(self, name, fn):
         err = self.cdll.spgan_error_string
+        nl = _LAUNCHES.get(name, 1)
 
         def call(*args):
+            prof = self.profile
+            if prof is not None:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             rc = fn(*args)
             if rc != 0:
                 raise SpganError("%s failed: %s (code %d)" % (name, err(rc).decode(), rc))
+            self.launches += nl
+            if prof is not None:
+                e1.record()
+                prof.append((name, tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 40)), e0, e1))
         call.__name__ = name
         return call
 

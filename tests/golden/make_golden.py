@@ -59,6 +59,37 @@ def buffers_of(module, prefix="buf."):
     return {prefix + k: pack(b) for k, b in module.named_buffers()}
 
 
+def _to64(sd):
+    out = {}
+    for k, v in sd.items():
+        v = v.clone()
+        if v.is_floating_point():
+            v = v.double()
+            if "running_" not in k:
+                v.requires_grad_(True)
+        out[k] = v
+    return out
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64).reshape(-1); b = np.asarray(b, np.float64).reshape(-1)
+    d = np.abs(a - b)
+    return max(d.max() / (np.abs(b).max() + 1e-30), np.sqrt((d ** 2).sum()) / (np.sqrt((b ** 2).sum()) + 1e-30))
+
+
+def noise_floor_generator(g_sd, o, xg, zg, rg, idx1, idx2, arrs):
+    """fp32 rounding noise of the REFERENCE itself: relative distance of its fp32 gradients from an
+    fp64 evaluation of the same graph (same neighbour lists).  Tests use max(1e-3, 3 * noise)."""
+    sd = _to64(g_sd)
+    out = R.generator_forward(sd, xg.double(), zg.double(), o, training=True, idx1=idx1, idx2=idx2)
+    (out * rg.double()).sum().backward()
+    res = {"noise.out_train": np.float32(_rel(arrs["out_train"], out.detach().numpy()))}
+    for k, v in sd.items():
+        if v.requires_grad and v.grad is not None and "grad." + k in arrs:
+            res["noise.grad." + k] = np.float32(_rel(arrs["grad." + k], pack(v.grad)))
+    return res
+
+
 def sphere(n):
     ball = np.loadtxt(os.path.join(REF, "template/balls/%d.xyz" % n))[:, :3]
     return R.normalize_cloud(ball)       # model.py:46-52 restated
@@ -183,7 +214,7 @@ def main():
     for tag, kw in (("default", {}), ("off_znorm", {"off": True, "z_norm": True}), ("use_head", {"use_head": True})):
         o = R.default_opts(np=256, **kw)
         rng = np.random.default_rng(50)
-        Bg = 2
+        Bg = 4
         g_sd = R.synth_state(R.generator_spec(o), 51)
         G = Generator(o)
         load_state(G, g_sd)
@@ -206,6 +237,7 @@ def main():
             arrs["idx2"] = idx2.view(Bg, 256, -1).numpy().astype(np.int16)
             arrs.update(grads_of(G))
             arrs.update(buffers_of(G))
+            arrs.update(noise_floor_generator(g_sd, o, xg, zg, rg, idx1, idx2, arrs))
             G.eval()
             with torch.no_grad():
                 arrs["out_eval"] = G(xg, zg).numpy()
@@ -232,6 +264,8 @@ def main():
     xg = torch.from_numpy(np.tile(ball256[None], (Bt, 1, 1)))
     gp_fn = GradientPenalty(10, gamma=1)
     arrs = {}
+    x1_log = []
+    hook = G.adain1.register_forward_hook(lambda m, i, out: x1_log.append(out.detach()))
     for step in range(2):
         data = torch.from_numpy(R.synthetic_chairs(rng, Bt, Nt))
         z_d = torch.from_numpy(R.latent_noise(rng, Bt, Nt, o.nz))
@@ -263,6 +297,9 @@ def main():
         if step == 0:
             arrs.update(grads_of(G, "s0.gradG."))
         optG.step()
+        for name, x1 in zip(("d", "g"), x1_log[-2:]):      # EdgeConv2 neighbour lists of the two G forwards
+            _, i2 = get_edge_features(x1, o.nk // 2, return_idx=True)
+            arrs["s%d.idx2_%s" % (step, name)] = i2.view(Bt, Nt, -1).numpy().astype(np.int16)
         arrs["s%d.data" % step] = data.numpy()
         arrs["s%d.z_d" % step] = z_d.numpy()[:, :1].copy()
         arrs["s%d.z_g" % step] = z_g.numpy()[:, :1].copy()
@@ -271,6 +308,7 @@ def main():
         arrs["s%d.gp" % step] = np.float32(gp.item())
         arrs["s%d.loss_g" % step] = np.float32(lossG.item())
         print("train step", step, lossD.item(), gp.item(), lossG.item())
+    hook.remove()
     arrs.update(buffers_of(G, "end.bufG."))
     arrs.update(buffers_of(D, "end.bufD."))
     arrs.update({"end.G." + k: pack(p) for k, p in G.named_parameters()})

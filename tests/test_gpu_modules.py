@@ -24,13 +24,23 @@ def _load(module, spec, seed):
 
 
 def _check_grads(module, g, prefix="grad.", tol=TOL):
+    """Per-parameter relative check.  Gradients that are mathematically zero (a conv bias feeding a
+    train-mode BatchNorm) are rounding noise in the reference too (~1e-6 of the layer's scale): they
+    are compared against the largest gradient magnitude of the module instead of their own."""
+    from conftest import pack_like_golden, rel_err
+    scale = max(float(np.abs(v).max()) for kk, v in g.items() if kk.startswith(prefix))
     n = 0
     for k, p in module.named_parameters():
         if prefix + k not in g:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, k
-        assert_rel(p.grad, g[prefix + k], tol, prefix + k)
+        ref = g[prefix + k]
+        if float(np.abs(ref).max()) < 1e-4 * scale:
+            got = pack_like_golden(p.grad)
+            assert float(np.abs(got - ref).max()) <= tol * 1e-2 * scale, (k, "noise-level gradient too large")
+        else:
+            assert_rel(p.grad, ref, tol, prefix + k)
         n += 1
     assert n > 0
 
@@ -130,7 +140,8 @@ def test_generator(tag, kw, sphere256):
     o = R.default_opts(np=256, **kw)
     G = _load(pkg.Generator(o), R.generator_spec(o), 51)
     G.train()
-    x = torch.from_numpy(np.tile(sphere256[None], (2, 1, 1))).cuda()
+    Bg = g["out_train"].shape[0]
+    x = torch.from_numpy(np.tile(sphere256[None], (Bg, 1, 1))).cuda()
     z = torch.from_numpy(np.tile(g["z"], (1, 256, 1))).cuda()
     if tag == "default":
         # kNN indices through the generator must be bit-exact where the input features are: EdgeConv1
@@ -138,22 +149,22 @@ def test_generator(tag, kw, sphere256):
         # not polluted by near-tie flips from ~1e-6 feature differences.
         G.debug_idx = (None, torch.from_numpy(g["idx2"].astype(np.int32)).cuda())
     out = G(x, z)
-    assert tuple(out.shape) == (2, 3, 256)
+    assert tuple(out.shape) == (Bg, 3, 256)
     if tag == "default":
         idx1 = G._graph_cache[1].cpu().numpy()
         assert np.array_equal(idx1, g["idx1"].astype(np.int32))
-        assert_rel(G._last_x1.view(2, 256, 64).permute(0, 2, 1), g["x1"], TOL, "x1")
+        assert_rel(G._last_x1.view(Bg, 256, 64).permute(0, 2, 1), g["x1"], TOL, "x1")
     assert_rel(out, g["out_train"], TOL, "out_train")
     if tag != "default":
         return
     _scalar_loss(out, torch.from_numpy(g["r"]).cuda()).backward()
-    _check_grads(G, g, tol=2e-3)
+    _check_grads(G, g)
     _check_bufs(G, g)
     # free-running kNN on our own features: flips only at near ties
     G.debug_idx = None
     G2 = _load(pkg.Generator(o), R.generator_spec(o), 51)
     G2.train()
-    out2 = G2(x, z.expand(2, 256, 128) if False else z)
+    out2 = G2(x, z)
     flips = float((out2 - out).abs().max())
     assert flips < 0.2, flips
     G.eval()
@@ -170,7 +181,7 @@ def test_generator_broadcast_latent_equals_tiled(sphere256):
     G = _load(pkg.Generator(o), R.generator_spec(o), 51)
     G.eval()
     x = torch.from_numpy(np.tile(sphere256[None], (2, 1, 1))).cuda()
-    zv = torch.from_numpy(golden("generator_default")["z"]).cuda()          # [2,1,128]
+    zv = torch.from_numpy(golden("generator_default")["z"]).cuda()[:2]      # [2,1,128]
     with torch.no_grad():
         a = G(x, zv.expand(2, 256, 128))
         b = G(x, zv.repeat(1, 256, 1))
@@ -182,10 +193,14 @@ def test_generator_interpolate(sphere256):
     g = golden("generator_default")
     o = R.default_opts(np=256)
     G = _load(pkg.Generator(o), R.generator_spec(o), 51)
-    G.eval()
-    x = torch.from_numpy(np.tile(sphere256[None], (2, 1, 1))).cuda()
+    Bg = g["out_train"].shape[0]
+    x = torch.from_numpy(np.tile(sphere256[None], (Bg, 1, 1))).cuda()
     z = torch.from_numpy(np.tile(g["z"], (1, 256, 1))).cuda()
     z2 = torch.from_numpy(np.tile(g["z2"], (1, 256, 1))).cuda()
+    G.train()
+    with torch.no_grad():
+        G(x, z)                          # the golden was taken after one train-mode forward (BN buffers)
+    G.eval()
     sel = torch.from_numpy(g["selection"]).cuda()
     with torch.no_grad():
         a = G.interpolate(x, z.clone(), z2, sel, 0.3)
@@ -208,12 +223,16 @@ def test_train_step_against_reference_golden(sphere256):
         tile = lambda a: torch.from_numpy(np.tile(a, (1, 256, 1))).cuda()
         real = torch.from_numpy(g["s%d.data" % step]).cuda().transpose(2, 1)
         alpha = torch.from_numpy(g["s%d.alpha" % step])
+        # inject the reference's EdgeConv2 neighbour lists: the step is chaotic w.r.t. near-tie flips
+        # (fp32 vs fp64 evaluation of the reference itself moves gp by 3.6 %), see DESIGN.md
+        G.debug_idx = (None, torch.from_numpy(g["s%d.idx2_d" % step].astype(np.int32)).cuda())
         loss_d, gp = tr.d_phase(x, tile(g["s%d.z_d" % step]), real, alpha)
         if step == 0:
             _check_grads(D, g, "s0.gradD.", tol=2e-3)
+        G.debug_idx = (None, torch.from_numpy(g["s%d.idx2_g" % step].astype(np.int32)).cuda())
         loss_g = tr.g_phase(x, tile(g["s%d.z_g" % step]), real)
         if step == 0:
-            _check_grads(G, g, "s0.gradG.", tol=5e-3)
+            _check_grads(G, g, "s0.gradG.", tol=2e-3)
         for key, val in (("loss_d", loss_d), ("gp", gp), ("loss_g", loss_g)):
             ref = float(g["s%d.%s" % (step, key)])
             assert abs(float(val) - ref) <= 2e-3 * max(1.0, abs(ref)), (step, key, float(val), ref)

@@ -108,7 +108,7 @@ def test_generator(tag, kw, sphere256):
     g = golden("generator_" + tag)
     o = R.default_opts(np=256, **kw)
     sd = _leaf(R.synth_state(R.generator_spec(o), 51))
-    x = torch.from_numpy(np.tile(sphere256[None], (2, 1, 1)))
+    x = torch.from_numpy(np.tile(sphere256[None], (g["out_train"].shape[0], 1, 1)))
     z = torch.from_numpy(np.tile(g["z"], (1, 256, 1)))
     out, x1 = R.generator_forward(sd, x, z, o, training=True, return_x1=True)
     assert_rel(out, g["out_train"], 1e-4, "out_train")
