@@ -213,9 +213,10 @@ int spgan_mean(const float *x, int64_t n, float scale, int accumulate, float *ou
 
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam semantics (model.py:94-97) over one flat parameter buffer: in-place update of
- * p, m, v from g; step is the 1-based step count. */
+ * p, m, v from grad_scale * g; step is the 1-based step count.  grad_scale = 1/world_size turns the
+ * summed all-reduce result into the data-parallel mean without a separate pass. */
 int spgan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
-                    float eps, int step, spgan_stream_t stream);
+                    float eps, int step, float grad_scale, spgan_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -276,9 +276,9 @@ __global__ void row_l2_normalize_kernel(const float* __restrict__ x, int64_t R, 
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2_sqrt) {
+                            float bc2_sqrt, float gscale) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gi = g[i];
+        const float gi = g[i] * gscale;
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;
@@ -402,12 +402,12 @@ extern "C" int spgan_row_l2_normalize(const float* x, int64_t R, int C, float ep
     return spgan_launch_status();
 }
 extern "C" int spgan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                               float beta2, float eps, int step, spgan_stream_t s) {
+                               float beta2, float eps, int step, float grad_scale, spgan_stream_t s) {
     SPGAN_CHECK_ARG(p && g && m && v && n >= 0 && step >= 1);
     if (n == 0) return SPGAN_OK;
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2 = 1.f - powf(beta2, (float)step);
-    adam_kernel<<<ew_grid(n, 256), 256, 0, as_stream(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+    adam_kernel<<<ew_grid(n, 256), 256, 0, as_stream(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
     return spgan_launch_status();
 }
 

@@ -9,10 +9,10 @@ with ONE NCCL all-reduce of a flat fp32 gradient buffer followed by a fused Adam
 the flat parameter buffer.
 """
 import torch
-import torch.distributed as dist
 
 from . import ops
 from .gradient_penalty import GradientPenalty
+from .parallel import FlatBuffers
 
 
 def requires_grad(model, flag=True):
@@ -32,44 +32,26 @@ def gen_loss_wgan(d_fake):
 
 
 class FlatAdam:
-    """torch.optim.Adam semantics over one flat buffer: parameters and gradients of a module are
-    re-pointed into two contiguous fp32 buffers so that the all-reduce and the update are one
-    collective and one kernel each."""
+    """torch.optim.Adam semantics (model.py:94-97) as ONE fused kernel over the flat parameter buffer,
+    preceded by ONE all-reduce of the flat gradient buffer when running data parallel."""
 
     def __init__(self, module, lr=1e-4, betas=(0.5, 0.99), eps=1e-8):
-        self.params = [p for p in module.parameters()]
-        n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
-        self.flat_g = ops.full((n,), 0.0, dev)
+        self.buf = FlatBuffers(module)
+        n, dev = self.buf.numel, self.buf.flat_p.device
         self.m = ops.full((n,), 0.0, dev)
         self.v = ops.full((n,), 0.0, dev)
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            ops.L().copy(p.data.contiguous().data_ptr(), self.flat_p[off:off + k].data_ptr(), k, ops._stream())
-            p.data = self.flat_p[off:off + k].view(p.shape)
-            p.grad = self.flat_g[off:off + k].view(p.shape)
-            off += k
         self.lr, self.betas, self.eps, self.t, self.n = lr, betas, eps, 0, n
 
     def zero_grad(self):
-        ops.fill_(self.flat_g, 0.0)
-        off = 0
-        for p in self.params:           # keep .grad pointing into the flat buffer
-            k = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * off:
-                p.grad = self.flat_g[off:off + k].view(p.shape)
-            off += k
+        ops.fill_(self.buf.flat_g, 0.0)
+        self.buf.rebind_grads()
 
-    def step(self, world_size=1):
-        if world_size > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-            ops.L().axpby(1.0 / world_size, self.flat_g.data_ptr(), 0.0, None, self.flat_g.data_ptr(), self.n,
-                          ops._stream())
+    def step(self):
+        scale = self.buf.allreduce_grads()
         self.t += 1
-        ops.L().adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                          self.n, self.lr, self.betas[0], self.betas[1], self.eps, self.t, ops._stream())
+        ops.L().adam_step(self.buf.flat_p.data_ptr(), self.buf.flat_g.data_ptr(), self.m.data_ptr(),
+                          self.v.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
+                          scale, ops._stream())
 
 
 class WGANGPTrainer:
@@ -80,7 +62,8 @@ class WGANGPTrainer:
         self.gp = GradientPenalty(lambda_gp, gamma=gamma)
         self.opt_g = FlatAdam(G, lr_g, betas)
         self.opt_d = FlatAdam(D, lr_d, betas)
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.opt_g.buf.broadcast_params()
+        self.opt_d.buf.broadcast_params()
 
     def d_phase(self, x, z, real, alpha=None):
         G, D = self.G, self.D
@@ -93,7 +76,7 @@ class WGANGPTrainer:
         gp = self.gp(D, real, fake, alpha=alpha)
         loss_d = ops.add(dis_loss_wgan(d_real, d_fake), gp)
         loss_d.backward()                             # model.py:259
-        self.opt_d.step(self.world)                   # model.py:260
+        self.opt_d.step()                   # model.py:260
         return loss_d.detach(), gp.detach()
 
     def g_phase(self, x, z, real):
@@ -106,7 +89,7 @@ class WGANGPTrainer:
             D(real)                                   # model.py:274: result unused, BN buffers still advance
         loss_g = gen_loss_wgan(D(fake))               # model.py:275-276
         loss_g.backward()                             # model.py:278
-        self.opt_g.step(self.world)                   # model.py:279
+        self.opt_g.step()                   # model.py:279
         return loss_g.detach()
 
     def step(self, x, z_d, z_g, real, alpha=None):

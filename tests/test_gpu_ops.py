@@ -377,5 +377,5 @@ def test_adam_matches_torch():
         pr.grad = g.clone()
         opt.step()
         gg = g.cuda()
-        ops.L().adam_step(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-4, 0.5, 0.99, 1e-8, t, None)
+        ops.L().adam_step(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-4, 0.5, 0.99, 1e-8, t, 1.0, None)
     close(p, pr.detach(), 1e-6)
