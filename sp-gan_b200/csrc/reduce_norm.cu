@@ -1,6 +1,7 @@
 // Column reductions, batch/instance normalisation (forward, backward, double backward),
 // poolings over points / neighbours, softmax over neighbours, edge aggregation, penalty.
 #include "common.cuh"
+#include "norm_fast.cuh"
 #include <float.h>
 
 namespace {
@@ -62,31 +63,57 @@ colreduce_partial_kernel(Op op, int C, int64_t seg_rows, int chunks, int64_t row
 
 template <int NV, typename Fin>
 __global__ void colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
+    // one warp per (segment, column): lanes stride over the row chunks, double-precision combine
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t total = nseg * C;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = warp; i < total; i += nwarps) {
         const int64_t seg = i / C;
         const int c = (int)(i - seg * C);
         double s[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) s[v] = 0.0;
-        for (int ch = 0; ch < chunks; ++ch)
+        for (int ch = lane; ch < chunks; ch += 32)
 #pragma unroll
-            for (int v = 0; v < NV; ++v) s[v] += (double)partial[(((seg * chunks) + ch) * NV + v) * C + c];
-        fin(seg, c, s);
+            for (int v = 0; v < NV; ++v) s[v] += (double)__ldg(partial + (((seg * chunks) + ch) * NV + v) * C + c);
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_xor_sync(0xffffffffu, s[v], o);
+        if (lane == 0) fin(seg, c, s);
     }
 }
 
-template <int NV, typename Op, typename Fin>
-int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStream_t st, Op op, Fin fin) {
+constexpr int kReduceTargetBlocks = 8 * kNumSMs;
+
+template <int NV, typename Op, typename Op4, typename Fin>
+int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStream_t st, Op op, Op4 op4, bool can_vec,
+                  Fin fin) {
     if (R <= 0) return SPGAN_OK;
     if (seg_rows < 1 || R % seg_rows != 0 || workspace == nullptr) return SPGAN_E_BADARG;
-    const ChunkPlan p = plan_chunks(R, C, seg_rows);
-    const int64_t gy = p.nseg * p.chunks;
-    if (gy > 65535) return SPGAN_E_UNSUPPORTED;
-    dim3 grid((C + 31) / 32, (unsigned)gy), block(32, 8);
     float* partial = reinterpret_cast<float*>(workspace);
-    colreduce_partial_kernel<NV><<<grid, block, 0, st>>>(op, C, seg_rows, p.chunks, p.rows_per_chunk, partial);
-    colreduce_final_kernel<NV><<<ew_grid(p.nseg * C, 128), 128, 0, st>>>(partial, C, p.nseg, p.chunks, fin);
+    int64_t nseg;
+    int chunks;
+    if (can_vec && C % 4 == 0) {
+        const int C4 = C / 4, TX = fastnorm::pick_tx(C4);
+        const fastnorm::Plan p = fastnorm::make_plan(R, C4, TX, seg_rows, kReduceTargetBlocks);
+        const int64_t gy = p.nseg * p.chunks;
+        if (gy > 65535) return SPGAN_E_UNSUPPORTED;
+        dim3 grid((C4 + TX - 1) / TX, (unsigned)gy);
+        if (TX == 32) fastnorm::colreduce4_kernel<NV, 32><<<grid, 256, 0, st>>>(op4, C4, seg_rows, p.chunks, p.rows_per_chunk, partial);
+        else if (TX == 16) fastnorm::colreduce4_kernel<NV, 16><<<grid, 256, 0, st>>>(op4, C4, seg_rows, p.chunks, p.rows_per_chunk, partial);
+        else fastnorm::colreduce4_kernel<NV, 8><<<grid, 256, 0, st>>>(op4, C4, seg_rows, p.chunks, p.rows_per_chunk, partial);
+        nseg = p.nseg; chunks = p.chunks;
+    } else {
+        const ChunkPlan p = plan_chunks(R, C, seg_rows);
+        const int64_t gy = p.nseg * p.chunks;
+        if (gy > 65535) return SPGAN_E_UNSUPPORTED;
+        dim3 grid((C + 31) / 32, (unsigned)gy), block(32, 8);
+        colreduce_partial_kernel<NV><<<grid, block, 0, st>>>(op, C, seg_rows, p.chunks, p.rows_per_chunk, partial);
+        nseg = p.nseg; chunks = p.chunks;
+    }
+    colreduce_final_kernel<NV><<<ew_grid(nseg * C * 32, 256), 256, 0, st>>>(partial, C, nseg, chunks, fin);
     return spgan_launch_status();
 }
 
@@ -155,6 +182,140 @@ struct Store5Fin {
     __device__ void operator()(int64_t, int c, const double* s) const {
 #pragma unroll
         for (int v = 0; v < 5; ++v) out[v * C + c] = (float)s[v];
+    }
+};
+
+// ---- float4 variants (see norm_fast.cuh): per-column parameters hoisted into State
+using fastnorm::ld4; using fastnorm::st4; using fastnorm::f4; using fastnorm::add4; using fastnorm::sub4;
+using fastnorm::mul4; using fastnorm::fma4; using fastnorm::mask4; using fastnorm::lrelu4;
+struct NoState {};
+struct SumOp4 {
+    const float* x; int C;
+    using State = NoState;
+    __device__ State init(int, int64_t) const { return State{}; }
+    __device__ void accum(const State&, int64_t r, int c4, float4* acc) const { acc[0] = add4(acc[0], ld4(x + r * C + c4 * 4)); }
+};
+struct DotOp4 {
+    const float* x; const float* y; int C;
+    using State = NoState;
+    __device__ State init(int, int64_t) const { return State{}; }
+    __device__ void accum(const State&, int64_t r, int c4, float4* acc) const {
+        acc[0] = fma4(ld4(x + r * C + c4 * 4), ld4(y + r * C + c4 * 4), acc[0]);
+    }
+};
+struct StatsOp4 {
+    const float* x; int C; int64_t seg_rows;
+    struct State { float4 shift; };
+    __device__ State init(int c4, int64_t seg) const { return State{ld4(x + seg * seg_rows * C + c4 * 4)}; }
+    __device__ void accum(const State& st, int64_t r, int c4, float4* acc) const {
+        const float4 d = sub4(ld4(x + r * C + c4 * 4), st.shift);
+        acc[0] = add4(acc[0], d); acc[1] = fma4(d, d, acc[1]);
+    }
+};
+struct NormBwdOp4 {
+    const float* g; const float* x; const float* y; float slope; int C; const float* mean; const float* rstd;
+    struct State { float4 mean, rstd; };
+    __device__ State init(int c4, int64_t seg) const { return State{ld4(mean + seg * C + c4 * 4), ld4(rstd + seg * C + c4 * 4)}; }
+    __device__ void accum(const State& st, int64_t r, int c4, float4* acc) const {
+        const int64_t i = r * C + c4 * 4;
+        float4 gi = ld4(g + i);
+        if (y != nullptr) gi = mask4(gi, ld4(y + i), slope);
+        const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
+        acc[0] = add4(acc[0], gi); acc[1] = fma4(gi, xh, acc[1]);
+    }
+};
+struct DblBwdOp4 {
+    const float* g; const float* u; const float* x; int C; const float* mean;
+    struct State { float4 mean; };
+    __device__ State init(int c4, int64_t) const { return State{ld4(mean + c4 * 4)}; }
+    __device__ void accum(const State& st, int64_t r, int c4, float4* acc) const {
+        const int64_t i = r * C + c4 * 4;
+        const float4 gi = ld4(g + i), ui = ld4(u + i), xm = sub4(ld4(x + i), st.mean);
+        acc[0] = add4(acc[0], gi); acc[1] = add4(acc[1], ui); acc[2] = fma4(gi, xm, acc[2]);
+        acc[3] = fma4(ui, xm, acc[3]); acc[4] = fma4(gi, ui, acc[4]);
+    }
+};
+// maps
+struct NormApplyOp4 {
+    const float* x; int C; const float* mean; const float* rstd; const float* gamma; const float* beta; float slope; float* y;
+    struct State { float4 mean, rstd, gamma, beta; };
+    __device__ State init(int c4, int64_t seg) const {
+        return State{ld4(mean + seg * C + c4 * 4), ld4(rstd + seg * C + c4 * 4),
+                     gamma ? ld4(gamma + c4 * 4) : f4(1.f), beta ? ld4(beta + c4 * 4) : f4(0.f)};
+    }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * C + c4 * 4;
+        float4 v = fma4(mul4(sub4(ld4(x + i), st.mean), st.rstd), st.gamma, st.beta);
+        if (slope != 1.f) v = lrelu4(v, slope);
+        st4(y + i, v);
+    }
+};
+struct NormBwdApplyOp4 {
+    const float* g; const float* x; const float* yact; float slope; int C; float inv_n; const float* mean;
+    const float* rstd; const float* gamma; const float* sg; const float* sgx; float* dx;
+    struct State { float4 mean, rstd, coef, a, b; };     // dx = coef * (g' - a - xh * b)
+    __device__ State init(int c4, int64_t seg) const {
+        const float4 m = ld4(mean + seg * C + c4 * 4), r = ld4(rstd + seg * C + c4 * 4);
+        const float4 gm = gamma ? ld4(gamma + c4 * 4) : f4(1.f);
+        return State{m, r, mul4(gm, r), mul4(ld4(sg + seg * C + c4 * 4), f4(inv_n)), mul4(ld4(sgx + seg * C + c4 * 4), f4(inv_n))};
+    }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * C + c4 * 4;
+        float4 gi = ld4(g + i);
+        if (yact != nullptr) gi = mask4(gi, ld4(yact + i), slope);
+        const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
+        st4(dx + i, mul4(st.coef, sub4(sub4(gi, st.a), mul4(xh, st.b))));
+    }
+};
+struct DblBwdApplyOp4 {
+    const float* g; const float* u; const float* x; int C; float inv_n; const float* mean; const float* rstd;
+    const float* gamma; const float* sums; float* gg; float* gx;
+    struct State { float4 mean, gm_r1, gm_r3, Su_n, Sg_n, Sux_n, Sgx_r3n, Sux_r3n, allsub_r3n; };
+    __device__ State init(int c4, int64_t) const {
+        const float4 r1 = ld4(rstd + c4 * 4);
+        const float4 r2 = mul4(r1, r1), r3 = mul4(r2, r1);
+        const float4 gm = gamma ? ld4(gamma + c4 * 4) : f4(1.f);
+        const float4 Sg = ld4(sums + c4 * 4), Su = ld4(sums + C + c4 * 4), Sgx = ld4(sums + 2 * C + c4 * 4),
+                     Sux = ld4(sums + 3 * C + c4 * 4), Sgu = ld4(sums + 4 * C + c4 * 4);
+        const float4 n = f4(inv_n);
+        // all_sub = Su*Sg/n - Sgu + 3 r^2 Sgx Sux / n
+        const float4 all_sub = add4(sub4(mul4(mul4(Su, Sg), n), Sgu), mul4(mul4(f4(3.f), r2), mul4(mul4(Sgx, Sux), n)));
+        return State{ld4(mean + c4 * 4), mul4(gm, r1), mul4(gm, r3), mul4(Su, n), mul4(Sg, n), mul4(Sux, n),
+                     mul4(mul4(Sgx, r3), n), mul4(mul4(Sux, r3), n), mul4(mul4(all_sub, r3), n)};
+    }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * C + c4 * 4;
+        const float4 gi = ld4(g + i), ui = ld4(u + i), xm = sub4(ld4(x + i), st.mean);
+        // gg = gm r1 (u - Su/n) - gm r3 xm Sux/n
+        st4(gg + i, sub4(mul4(st.gm_r1, sub4(ui, st.Su_n)), mul4(mul4(st.gm_r3, xm), st.Sux_n)));
+        // gx = gm/r3-scaled terms: gm * (xm r3 all_sub/n + Sux r3/n (Sg/n - g) + Sgx r3/n (Su/n - u)); gm folded via gm_r1/r1
+        const float4 t0 = mul4(xm, st.allsub_r3n);
+        const float4 t1 = mul4(st.Sux_r3n, sub4(st.Sg_n, gi));
+        const float4 t2 = mul4(st.Sgx_r3n, sub4(st.Su_n, ui));
+        const float4 gmv = gamma ? ld4(gamma + c4 * 4) : f4(1.f);
+        st4(gx + i, mul4(gmv, add4(add4(t0, t1), t2)));
+    }
+};
+struct AdainApplyOp4 {
+    const float* x; const float* s; int C; const float* mean; const float* rstd; float* out;
+    struct State { float4 mean, rstd; };
+    __device__ State init(int c4, int64_t seg) const { return State{ld4(mean + seg * C + c4 * 4), ld4(rstd + seg * C + c4 * 4)}; }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * C + c4 * 4;
+        const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
+        st4(out + i, fma4(ld4(s + r * 2 * C + c4 * 4), xh, ld4(s + r * 2 * C + C + c4 * 4)));
+    }
+};
+struct AdainBwdOp4 {
+    const float* g; const float* x; const float* s; int C; const float* mean; const float* rstd; float* ds; float* gxh;
+    struct State { float4 mean, rstd; };
+    __device__ State init(int c4, int64_t seg) const { return State{ld4(mean + seg * C + c4 * 4), ld4(rstd + seg * C + c4 * 4)}; }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * C + c4 * 4;
+        const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
+        const float4 gi = ld4(g + i);
+        if (ds) { st4(ds + r * 2 * C + c4 * 4, mul4(gi, xh)); st4(ds + r * 2 * C + C + c4 * 4, gi); }
+        if (gxh) st4(gxh + i, mul4(gi, ld4(s + r * 2 * C + c4 * 4)));
     }
 };
 
@@ -524,23 +685,30 @@ __global__ void mean_kernel(const float* __restrict__ x, int64_t n, float scale,
 extern "C" size_t spgan_colreduce_workspace(int64_t R, int C, int64_t seg_rows, int nvals) {
     if (R <= 0 || C <= 0 || seg_rows <= 0 || nvals <= 0 || R % seg_rows != 0) return 0;
     const ChunkPlan p = plan_chunks(R, C, seg_rows);
-    return (size_t)p.nseg * p.chunks * nvals * C * sizeof(float);
+    size_t n = (size_t)p.nseg * p.chunks;
+    if (C % 4 == 0) {
+        const fastnorm::Plan q = fastnorm::make_plan(R, C / 4, fastnorm::pick_tx(C / 4), seg_rows, kReduceTargetBlocks);
+        const size_t m = (size_t)q.nseg * q.chunks;
+        if (m > n) n = m;
+    }
+    return n * nvals * C * sizeof(float);
 }
 
 extern "C" int spgan_colsum(const float* x, int64_t R, int C, int64_t seg_rows, float* out, void* ws,
                             spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && out && R >= 0 && C >= 1);
-    return run_colreduce<1>(R, C, seg_rows, ws, as_stream(s), SumOp{x, C}, Store1Fin{out, C});
+    return run_colreduce<1>(R, C, seg_rows, ws, as_stream(s), SumOp{x, C}, SumOp4{x, C}, al16(x), Store1Fin{out, C});
 }
 extern "C" int spgan_coldot(const float* x, const float* y, int64_t R, int C, int64_t seg_rows, float* out,
                             void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && y && out && R >= 0 && C >= 1);
-    return run_colreduce<1>(R, C, seg_rows, ws, as_stream(s), DotOp{x, y, C}, Store1Fin{out, C});
+    return run_colreduce<1>(R, C, seg_rows, ws, as_stream(s), DotOp{x, y, C}, DotOp4{x, y, C}, al16(x) && al16(y),
+                            Store1Fin{out, C});
 }
 extern "C" int spgan_colstats(const float* x, int64_t R, int C, int64_t seg_rows, float eps, float* mean,
                               float* rstd, float* var, void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && mean && rstd && R >= 1 && C >= 1);
-    return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), StatsOp{x, C, seg_rows},
+    return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), StatsOp{x, C, seg_rows}, StatsOp4{x, C, seg_rows}, al16(x),
                             StatsFin{x, C, seg_rows, eps, mean, rstd, var});
 }
 extern "C" int spgan_norm_apply(const float* x, int64_t R, int C, int64_t seg_rows, const float* mean,
@@ -548,6 +716,9 @@ extern "C" int spgan_norm_apply(const float* x, int64_t R, int C, int64_t seg_ro
                                 spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && mean && rstd && y && R >= 0 && C >= 1 && seg_rows >= 1);
     if (R == 0) return SPGAN_OK;
+    if (C % 4 == 0 && R % seg_rows == 0 && al16(x) && al16(y) && al16(mean) && al16(rstd) && (!gamma || al16(gamma)) &&
+        (!beta || al16(beta)))
+        return fastnorm::run_map(R, C, seg_rows, as_stream(s), NormApplyOp4{x, C, mean, rstd, gamma, beta, slope, y});
     norm_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(x, R, C, seg_rows, mean, rstd, gamma, beta,
                                                                          slope, y);
     return spgan_launch_status();
@@ -563,14 +734,19 @@ extern "C" int spgan_norm_bwd_reduce(const float* g, const float* x, const float
                                      int C, int64_t seg_rows, const float* mean, const float* rstd, float* sg,
                                      float* sgx, void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && R >= 1 && C >= 1);
+    const bool vec = al16(g) && al16(x) && al16(mean) && al16(rstd) && (!y_act || al16(y_act));
     return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), NormBwdOp{g, x, y_act, slope, C, mean, rstd},
-                            Store2Fin{sg, sgx, C});
+                            NormBwdOp4{g, x, y_act, slope, C, mean, rstd}, vec, Store2Fin{sg, sgx, C});
 }
 extern "C" int spgan_norm_bwd_apply(const float* g, const float* x, const float* y_act, float slope, int64_t R,
                                     int C, int64_t seg_rows, const float* mean, const float* rstd,
                                     const float* gamma, const float* sg, const float* sgx, float* dx,
                                     spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && dx && R >= 1 && C >= 1 && seg_rows >= 1);
+    if (C % 4 == 0 && R % seg_rows == 0 && al16(g) && al16(x) && al16(dx) && al16(mean) && al16(rstd) && al16(sg) &&
+        al16(sgx) && (!gamma || al16(gamma)) && (!y_act || al16(y_act)))
+        return fastnorm::run_map(R, C, seg_rows, as_stream(s),
+                                 NormBwdApplyOp4{g, x, y_act, slope, C, 1.f / (float)seg_rows, mean, rstd, gamma, sg, sgx, dx});
     norm_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, x, y_act, slope, R, C, seg_rows, mean,
                                                                              rstd, gamma, sg, sgx, dx);
     return spgan_launch_status();
@@ -578,14 +754,22 @@ extern "C" int spgan_norm_bwd_apply(const float* g, const float* x, const float*
 extern "C" int spgan_bn_dbl_bwd_reduce(const float* g, const float* u, const float* x, int64_t R, int C,
                                        const float* mean, float* sums, void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && u && x && mean && sums && R >= 1 && C >= 1);
-    return run_colreduce<5>(R, C, R, ws, as_stream(s), DblBwdOp{g, u, x, C, mean}, Store5Fin{sums, C});
+    return run_colreduce<5>(R, C, R, ws, as_stream(s), DblBwdOp{g, u, x, C, mean}, DblBwdOp4{g, u, x, C, mean},
+                            al16(g) && al16(u) && al16(x) && al16(mean), Store5Fin{sums, C});
 }
 extern "C" int spgan_bn_dbl_bwd_apply(const float* g, const float* u, const float* x, int64_t R, int C,
                                       const float* mean, const float* rstd, const float* gamma, const float* sums,
                                       float* gg, float* gx, float* ggamma, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && u && x && mean && rstd && sums && gg && gx && R >= 1 && C >= 1);
-    bn_dbl_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, u, x, R, C, mean, rstd, gamma, sums,
-                                                                               gg, gx);
+    if (C % 4 == 0 && al16(g) && al16(u) && al16(x) && al16(gg) && al16(gx) && al16(mean) && al16(rstd) && al16(sums) &&
+        (!gamma || al16(gamma))) {
+        int rc = fastnorm::run_map(R, C, R, as_stream(s),
+                                   DblBwdApplyOp4{g, u, x, C, 1.f / (float)R, mean, rstd, gamma, sums, gg, gx});
+        if (rc != SPGAN_OK) return rc;
+    } else {
+        bn_dbl_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, u, x, R, C, mean, rstd, gamma, sums,
+                                                                                   gg, gx);
+    }
     if (ggamma) bn_dbl_bwd_gamma_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(C, R, rstd, sums, ggamma);
     return spgan_launch_status();
 }
@@ -668,6 +852,8 @@ extern "C" int spgan_adain_apply(const float* x, const float* sv, int64_t R, int
                                  const float* mean, const float* rstd, float* out, spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && sv && mean && rstd && out && R >= 0 && C >= 1 && seg_rows >= 1);
     if (R == 0) return SPGAN_OK;
+    if (C % 4 == 0 && R % seg_rows == 0 && al16(x) && al16(sv) && al16(out) && al16(mean) && al16(rstd))
+        return fastnorm::run_map(R, C, seg_rows, as_stream(s), AdainApplyOp4{x, sv, C, mean, rstd, out});
     adain_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(x, sv, R, C, seg_rows, mean, rstd, out);
     return spgan_launch_status();
 }
@@ -675,6 +861,9 @@ extern "C" int spgan_adain_bwd(const float* g, const float* x, const float* sv, 
                                const float* mean, const float* rstd, float* ds, float* gxh, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && x && sv && mean && rstd && R >= 0 && C >= 1 && seg_rows >= 1);
     if (R == 0) return SPGAN_OK;
+    if (C % 4 == 0 && R % seg_rows == 0 && al16(g) && al16(x) && al16(sv) && al16(mean) && al16(rstd) &&
+        (!ds || al16(ds)) && (!gxh || al16(gxh)))
+        return fastnorm::run_map(R, C, seg_rows, as_stream(s), AdainBwdOp4{g, x, sv, C, mean, rstd, ds, gxh});
     adain_bwd_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, x, sv, R, C, seg_rows, mean, rstd, ds, gxh);
     return spgan_launch_status();
 }

@@ -20,6 +20,9 @@ def shard_bounds(total, rank, world):
     return rank * per, (rank + 1) * per
 
 
+ALIGN_ELEMS = 64          # 256 bytes
+
+
 class FlatBuffers:
     """Re-points every parameter of `module` (and its .grad) into two contiguous fp32 buffers.
     Layout = parameter registration order, so all ranks agree on offsets."""
@@ -29,19 +32,22 @@ class FlatBuffers:
         if not self.params:
             raise ValueError("module has no parameters")
         dev = self.params[0].device
-        self.numel = sum(p.numel() for p in self.params)
-        self.flat_p = torch.empty(self.numel, device=dev, dtype=torch.float32)
+        # every parameter starts on a 256-byte boundary so that kernels keep their vectorised
+        # (16-byte) access paths on the re-pointed weights; the padding stays zero forever
+        # (zero gradient -> Adam leaves it at zero).
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
+        self.numel = off
+        self.flat_p = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(self.numel, device=dev, dtype=torch.float32)
-        self.offsets = []
-        off = 0
         with torch.no_grad():
-            for p in self.params:
+            for p, off in zip(self.params, self.offsets):
                 k = p.numel()
                 self.flat_p[off:off + k].copy_(p.data.reshape(-1))      # one-time re-layout at construction
                 p.data = self.flat_p[off:off + k].view(p.shape)
                 p.grad = self.flat_g[off:off + k].view(p.shape)
-                self.offsets.append(off)
-                off += k
 
     def rebind_grads(self):
         """Autograd keeps accumulating into .grad in place; re-attach any that were dropped."""
