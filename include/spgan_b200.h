@@ -86,11 +86,17 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  * likewise B stored [K,N] (transB=0) or [N,K] (transB=1).  Replaces every Conv1d(k=1) /
  * Conv2d(1x1) / Conv2d([1,k]) / Linear of Generator.py:56-71,107-135 and
  * Discriminator.py:55-94 and their autograd (dgrad: NN, wgrad: TN with split-K).
- * engine: 0 = fp32 CUDA-core tiles; 1 = tcgen05 tensor cores (bf16x3 split, fp32 accumulate
- * in TMEM) where the shape allows, else falls back to 0. */
+ * engine: 0 = fp32 CUDA-core tiles (exact fp32 products, sequential-k accumulation per tile);
+ *         1 = tcgen05 tensor cores: operands split into bf16 hi+lo, three MMAs per product term
+ *             (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM; ~2^-16 relative per product.
+ *             Needs transA == 0, M >= 128, N >= 16, K >= 16 and a workspace of
+ *             spgan_gemm_workspace(1, N, K) bytes (256-byte aligned); otherwise engine 0 runs.
+ * The first int of the workspace is a status word: non-zero after completion means the kernel
+ * aborted on an internal pipeline timeout (never expected; checked by the tests). */
+size_t spgan_gemm_workspace(int engine, int N, int K);
 int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float *A, int64_t lda, const float *B,
-               int64_t ldb, float *C, int64_t ldc, const float *bias, int accumulate, int engine,
-               spgan_stream_t stream);
+               int64_t ldb, float *C, int64_t ldc, const float *bias, int accumulate, int engine, void *workspace,
+               size_t workspace_bytes, spgan_stream_t stream);
 
 /* ------------------------------------------------------------------ elementwise
  * n = element count of flat fp32 tensors unless rows/cols are given. */

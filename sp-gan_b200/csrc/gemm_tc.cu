@@ -1,0 +1,393 @@
+// tcgen05 GEMM (engine 1 of spgan_gemm): C[M,N] = A[M,K] * B^T (+bias) (+C), fp32 in / fp32 out.
+//
+// Precision: every fp32 operand is split into two bf16 terms (hi = truncation, lo = rn(x - hi)) and
+// the product is formed as Ahi*Bhi + Ahi*Blo + Alo*Bhi on the 5th-gen tensor cores with fp32
+// accumulation in TMEM ("bf16x3", ~2^-16 relative per product; the dropped lo*lo term is 2^-16).
+//
+// Structure (one persistent CTA per SM, 13 warps):
+//   warps 0-3   epilogue : tcgen05.ld accumulator rows from TMEM -> (+bias, +C) -> global
+//   warp  4     MMA      : one lane issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and commits
+//   warps 5-12  producer : global fp32 A tile -> split -> 128B-swizzled K-major shared tiles;
+//                          pre-split bf16 B tiles -> shared.  (No TMA: the A operand needs the
+//                          fp32 -> 2 x bf16 conversion on the way in.)
+// Pipelines: full/empty mbarriers per shared stage, tmem_full/tmem_empty per accumulator buffer
+// (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
+// Every mbarrier wait is bounded; on timeout the kernel raises a status word instead of hanging.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                      // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int MMA_WARP = 4;
+constexpr int PROD_WARP0 = 5;
+constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_PROD_THREADS = NUM_PROD_WARPS * 32;
+constexpr int TC_THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;     // 416
+constexpr uint32_t SPIN_LIMIT = 1u << 20;
+
+template <int BN>
+struct Cfg {
+    static constexpr int A_BYTES = BM * 128;             // one half (hi or lo)
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int TMEM_COLS = 2 * BN;             // 128 / 256 / 512: powers of two
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: returns false if the kernel must abort (deadlock guard; sets *status)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* status) {
+    for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((it & 0xfff) == 0xfff && *status != 0) return false;
+    }
+    atomicExch((int*)status, 1);
+    return false;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address            bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset       bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// 8 fp32 -> 8 bf16 "hi" (truncation) + 8 bf16 "lo" (rn of the remainder), element 0 in the low half
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t u0 = __float_as_uint(v[2 * i]), u1 = __float_as_uint(v[2 * i + 1]);
+        h[i] = __byte_perm(u0, u1, 0x7632);
+        const float r0 = v[2 * i] - __uint_as_float(u0 & 0xffff0000u);
+        const float r1 = v[2 * i + 1] - __uint_as_float(u1 & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
+               const uint16_t* __restrict__ Bhi, const uint16_t* __restrict__ Blo, int Kp, int n_tiles,
+               float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int accumulate, int* status,
+               bool vecA, bool vecC) {
+    using cfg = Cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
+    // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * cfg::STAGES + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (cfg::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * cfg::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * cfg::STAGES + 2 + a); };
+
+    if (tid == 0) {
+        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_THREADS); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t m_tiles = (M + BM - 1) / BM;
+    const int64_t total_tiles = m_tiles * n_tiles;
+    const int KB = Kp / BK;
+    volatile int* vstatus = status;
+
+    if (warp >= PROD_WARP0) {
+        // ================================================================ producers
+        const int ptid = tid - PROD_WARP0 * 32;
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+            const int64_t m0 = (t / n_tiles) * BM;
+            const int n0 = (int)(t % n_tiles) * BN;
+            for (int kb = 0; kb < KB; ++kb) {
+                if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) { ok = false; break; }
+                unsigned char* sa_hi = smem + stage * cfg::STAGE_BYTES;
+                unsigned char* sa_lo = sa_hi + cfg::A_BYTES;
+                unsigned char* sb_hi = sa_lo + cfg::A_BYTES;
+                unsigned char* sb_lo = sb_hi + cfg::B_BYTES;
+                const int k0 = kb * BK;
+                const bool fullk = vecA && (k0 + BK <= K);
+                // ---- A: 128 rows x 8 chunks of 8 fp32
+#pragma unroll 2
+                for (int task = ptid; task < BM * 8; task += NUM_PROD_THREADS) {
+                    const int row = task >> 3, ch = task & 7;
+                    int64_t gm = m0 + row;
+                    if (gm >= M) gm = M - 1;                   // clamp: rows beyond M are never stored
+                    const float* src = A + gm * lda + k0 + ch * 8;
+                    float v[8];
+                    if (fullk) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = (k0 + ch * 8 + j < K) ? __ldg(src + j) : 0.f;
+                    }
+                    uint4 hi, lo;
+                    split8(v, hi, lo);
+                    const uint32_t off = swz(row, ch);
+                    *reinterpret_cast<uint4*>(sa_hi + off) = hi;
+                    *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+                }
+                // ---- B: BN rows x 8 chunks of 8 bf16, both halves (already split and zero padded)
+#pragma unroll 2
+                for (int task = ptid; task < BN * 8; task += NUM_PROD_THREADS) {
+                    const int row = task >> 3, ch = task & 7;
+                    const size_t e = (size_t)(n0 + row) * Kp + k0 + ch * 8;
+                    const uint4 h = __ldg(reinterpret_cast<const uint4*>(Bhi + e));
+                    const uint4 l = __ldg(reinterpret_cast<const uint4*>(Blo + e));
+                    const uint32_t off = swz(row, ch);
+                    *reinterpret_cast<uint4*>(sb_hi + off) = h;
+                    *reinterpret_cast<uint4*>(sb_lo + off) = l;
+                }
+                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(full_bar(stage));
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================================================================ MMA issuer
+        constexpr uint32_t idesc = make_idesc(BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        bool ok = true;
+        for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+            if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1, vstatus)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                if (!mbar_wait(full_bar(stage), phase, vstatus)) { ok = false; break; }
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa_hi = smem_u32(smem + stage * cfg::STAGE_BYTES);
+                    const uint32_t sa_lo = sa_hi + cfg::A_BYTES;
+                    const uint32_t sb_hi = sa_lo + cfg::A_BYTES;
+                    const uint32_t sb_lo = sb_hi + cfg::B_BYTES;
+                    const uint64_t dah = make_desc(sa_hi), dal = make_desc(sa_lo);
+                    const uint64_t dbh = make_desc(sb_hi), dbl = make_desc(sb_lo);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t adv = (uint64_t)(kk * 2);          // 32 bytes per K=16 step, >>4
+                        umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                        umma_bf16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+                        umma_bf16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(stage));        // frees the stage once the MMAs have read it
+                }
+                __syncwarp();
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (!ok) break;
+            if (lane == 0) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            __syncwarp();
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        // ================================================================ epilogue (warps 0..3)
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        bool ok = true;
+        for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+            const int64_t m0 = (t / n_tiles) * BM;
+            const int n0 = (int)(t % n_tiles) * BN;
+            if (!mbar_wait(tfull_bar(acc), acc_phase, vstatus)) { ok = false; break; }
+            tc_fence_after();
+            const int64_t row = m0 + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+            float* crow = C + row * ldc + n0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);               // all lanes participate (sync.aligned)
+                if (row < M && n0 + c0 < N) {
+                    if (vecC && n0 + c0 + 16 <= N) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            if (bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
+                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            }
+                            if (accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(crow + c0 + 4 * q);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = n0 + c0 + j;
+                            if (col < N) {
+                                float o = v[j];
+                                if (bias) o += __ldg(bias + col);
+                                if (accumulate) o += crow[c0 + j];
+                                crow[c0 + j] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, cfg::TMEM_COLS);
+    }
+}
+
+// B (weights) -> zero-padded bf16 hi / lo, K-major [Npad, Kp]; also clears the status word
+__global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int transB, int N, int K, int Npad, int Kp,
+                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int* status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
+    const int64_t total = (int64_t)Npad * Kp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / Kp), k = (int)(i % Kp);
+        float v = 0.f;
+        if (n < N && k < K) v = transB ? __ldg(B + (int64_t)n * ldb + k) : __ldg(B + (int64_t)k * ldb + n);
+        const uint32_t u = __float_as_uint(v);
+        const float r = v - __uint_as_float(u & 0xffff0000u);
+        uint32_t l2;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(0.f), "f"(r));
+        hi[i] = (uint16_t)(u >> 16);
+        lo[i] = (uint16_t)(l2 & 0xffffu);
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <int BN>
+int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const uint16_t* hi, const uint16_t* lo, int Kp,
+              int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
+    using cfg = Cfg<BN>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const int n_tiles = Npad / BN;
+    const int64_t total = ((M + BM - 1) / BM) * n_tiles;
+    const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+    const bool vecA = (lda % 4 == 0) && aligned16(A);
+    const bool vecC = (ldc % 4 == 0) && aligned16(C) && (bias == nullptr || aligned16(bias));
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc, bias,
+                                                                   accumulate, status, vecA, vecC);
+    return spgan_launch_status();
+}
+
+}  // namespace
+
+size_t spgan_gemm_tc_workspace(int N, int K) {
+    const size_t Npad = align_up((size_t)N, 256), Kp = align_up((size_t)K, BK);
+    return 256 + 2 * align_up(Npad * Kp * sizeof(uint16_t), 256);
+}
+
+bool spgan_gemm_tc_supported(int transA, int64_t M, int N, int K) {
+    return !transA && M >= 128 && N >= 16 && K >= 16;
+}
+
+int spgan_gemm_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                  float* C, int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st) {
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const int Npad = (int)align_up((size_t)N, BN), Kp = (int)align_up((size_t)K, BK);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    int* status = reinterpret_cast<int*>(ws);
+    uint16_t* hi = reinterpret_cast<uint16_t*>(ws + 256);
+    uint16_t* lo = reinterpret_cast<uint16_t*>(ws + 256 + align_up(align_up((size_t)N, 256) * Kp * sizeof(uint16_t), 256));
+    presplit_b_kernel<<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, Npad, Kp, hi, lo, status);
+    int rc = spgan_launch_status();
+    if (rc != SPGAN_OK) return rc;
+    if (BN == 64) return launch_tc<64>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    if (BN == 128) return launch_tc<128>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    return launch_tc<256>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+}

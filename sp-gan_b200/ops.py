@@ -131,7 +131,11 @@ def _gemm_operand(t):
 # =========================================================================================
 # dense contraction
 # =========================================================================================
-def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False):
+LAST_TC_WORKSPACE = None      # most recent tcgen05 workspace (its first int is the kernel's status word)
+
+
+def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, engine=None):
+    global LAST_TC_WORKSPACE
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
     M = A.shape[1] if ta else A.shape[0]
@@ -144,8 +148,15 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False):
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     if bias is not None:
         bias = _c(bias)
+    engine = GEMM_ENGINE if engine is None else engine
+    ws, ws_bytes = None, 0
+    if engine == 1 and not ta and M >= 128 and N >= 16 and K >= 16:
+        ws_bytes = L().gemm_workspace(1, N, K)
+        ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
+        LAST_TC_WORKSPACE = ws
     L().gemm(int(ta), int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
-             bias.data_ptr() if bias is not None else None, int(accumulate), GEMM_ENGINE, _stream())
+             bias.data_ptr() if bias is not None else None, int(accumulate), engine,
+             ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
     return out
 
 

@@ -40,7 +40,7 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(m.SpganError):
         L.knn_group(None, None, 1, 3, 16, 4, None, None, None)
     with pytest.raises(m.SpganError):
-        L.gemm(0, 0, 4, 4, 4, None, 4, None, 4, None, 4, None, 0, 0, None)
+        L.gemm(0, 0, 4, 4, 4, None, 4, None, 4, None, 4, None, 0, 0, None, 0, None)
     assert L.cdll.spgan_knn_group(1, 1, 1, 3, 64, 40, 1, None, None) == -2     # k + 1 > 32
     assert L.cdll.spgan_knn_group(1, 1, 1, 3, 4, 4, 1, None, None) == -1      # k + 1 > N
     assert L.colreduce_workspace(0, 4, 1, 1) == 0

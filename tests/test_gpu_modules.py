@@ -235,7 +235,11 @@ def test_train_step_against_reference_golden(sphere256):
             _check_grads(G, g, "s0.gradG.", tol=5e-3, max_tol=5e-2)
         for key, val in (("loss_d", loss_d), ("gp", gp), ("loss_g", loss_g)):
             ref = float(g["s%d.%s" % (step, key)])
-            assert abs(float(val) - ref) <= 2e-3 * max(1.0, abs(ref)), (step, key, float(val), ref)
+            # step 0 is a pure forward of the initial weights.  Step 1 follows one Adam update whose very first
+            # step moves every weight by +-lr * sign(grad) regardless of |grad|: parameters with noise-level
+            # gradients get rounding-dependent signs, so the second step is only loosely comparable.
+            tol = 2e-3 if step == 0 else 1e-2
+            assert abs(float(val) - ref) <= tol * max(1.0, abs(ref)), (step, key, float(val), ref)
     for k, b in D.named_buffers():
         if k.endswith("num_batches_tracked"):
             assert int(b) == int(g["end.bufD." + k])
