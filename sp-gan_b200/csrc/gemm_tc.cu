@@ -4,12 +4,14 @@
 // the product is formed as Ahi*Bhi + Ahi*Blo + Alo*Bhi on the 5th-gen tensor cores with fp32
 // accumulation in TMEM ("bf16x3", ~2^-16 relative per product; the dropped lo*lo term is 2^-16).
 //
-// Structure (one persistent CTA per SM, 13 warps):
-//   warps 0-3   epilogue : tcgen05.ld accumulator rows from TMEM -> (+bias, +C) -> global
+// Structure (one persistent CTA per SM, 15 warps):
+//   warps 0-3   epilogue : tcgen05.ld accumulator rows from TMEM -> shared transpose -> (+bias, +C)
+//                          -> 128-byte coalesced global stores
 //   warp  4     MMA      : one lane issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and commits
-//   warps 5-12  producer : global fp32 A tile -> split -> 128B-swizzled K-major shared tiles;
-//                          pre-split bf16 B tiles -> shared.  (No TMA: the A operand needs the
-//                          fp32 -> 2 x bf16 conversion on the way in.)
+//   warps 5-12  A producer: global fp32 A tile -> split -> 128B-swizzled K-major shared tiles, with
+//                          the next k-block's loads in flight during conversion.  (No TMA: the A
+//                          operand needs the fp32 -> 2 x bf16 conversion on the way in.)
+//   warps 13-14 B loader : pre-split bf16 weight tiles -> shared with cp.async (from L2)
 // Pipelines: full/empty mbarriers per shared stage, tmem_full/tmem_empty per accumulator buffer
 // (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
 // Every mbarrier wait is bounded; on timeout the kernel raises a status word instead of hanging.
@@ -21,10 +23,12 @@ constexpr int BM = 128;
 constexpr int BK = 64;                      // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
-constexpr int PROD_WARP0 = 5;
-constexpr int NUM_PROD_WARPS = 8;
-constexpr int NUM_PROD_THREADS = NUM_PROD_WARPS * 32;
-constexpr int TC_THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;     // 416
+constexpr int A_WARP0 = 5;                  // 8 warps convert the fp32 A operand
+constexpr int NUM_A_THREADS = 8 * 32;
+constexpr int B_WARP0 = 13;                 // 2 warps stream the pre-split bf16 B operand (cp.async)
+constexpr int NUM_B_THREADS = 2 * 32;
+constexpr int TC_THREADS = 15 * 32;         // 480
+constexpr int EPI_LD = 36;                  // padded row stride (floats) of the epilogue staging tile
 constexpr uint32_t SPIN_LIMIT = 1u << 20;
 
 template <int BN>
@@ -34,7 +38,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
     static constexpr int TMEM_COLS = 2 * BN;             // 128 / 256 / 512: powers of two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                      NUM_EPI_WARPS * 32 * 36 * 4 /*epilogue staging*/;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -150,6 +155,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
     // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * cfg::STAGES + 4);
+    float* epi_smem = reinterpret_cast<float*>(smem + cfg::STAGES * cfg::STAGE_BYTES + 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -159,7 +165,10 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * cfg::STAGES + 2 + a); };
 
     if (tid == 0) {
-        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(full_bar(s), NUM_PROD_THREADS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < cfg::STAGES; ++s) {
+            mbar_init(full_bar(s), NUM_A_THREADS + NUM_B_THREADS);
+            mbar_init(empty_bar(s), 1);
+        }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -174,57 +183,94 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     const int KB = Kp / BK;
     volatile int* vstatus = status;
 
-    if (warp >= PROD_WARP0) {
-        // ================================================================ producers
-        const int ptid = tid - PROD_WARP0 * 32;
+    if (warp >= A_WARP0 && warp < B_WARP0) {
+        // ================================================================ A producers (fp32 -> bf16 hi/lo)
+        // Each thread owns 4 (row, 8-float chunk) tasks of a k-block; the loads of the NEXT k-block are
+        // issued before the current one is converted, so HBM latency overlaps conversion and the wait
+        // for a free stage.
+        constexpr int TASKS = BM * 8 / NUM_A_THREADS;          // 4
+        const int ptid = tid - A_WARP0 * 32;
+        float4 cur[2 * TASKS], nxt[2 * TASKS];
+        auto load_a = [&](int64_t t, int kb, float4* r) {
+            const int64_t m0 = (t / n_tiles) * BM;
+            const int k0 = kb * BK;
+            const bool fullk = vecA && (k0 + BK <= K);
+#pragma unroll
+            for (int j = 0; j < TASKS; ++j) {
+                const int task = ptid + j * NUM_A_THREADS;
+                const int row = task >> 3, ch = task & 7;
+                int64_t gm = m0 + row;
+                if (gm >= M) gm = M - 1;                       // clamp: rows beyond M are never stored
+                const float* src = A + gm * lda + k0 + ch * 8;
+                if (fullk) {
+                    r[2 * j] = __ldg(reinterpret_cast<const float4*>(src));
+                    r[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                } else {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = (k0 + ch * 8 + e < K) ? __ldg(src + e) : 0.f;
+                    r[2 * j] = make_float4(v[0], v[1], v[2], v[3]);
+                    r[2 * j + 1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        int64_t t = blockIdx.x;
+        int kb = 0;
+        bool have = t < total_tiles;
+        if (have) load_a(t, kb, cur);
+        while (have) {
+            int64_t tn = t;
+            int kbn = kb + 1;
+            if (kbn == KB) { kbn = 0; tn += gridDim.x; }
+            const bool have_next = tn < total_tiles;
+            if (have_next) load_a(tn, kbn, nxt);
+            if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) break;
+            unsigned char* sa_hi = smem + stage * cfg::STAGE_BYTES;
+            unsigned char* sa_lo = sa_hi + cfg::A_BYTES;
+#pragma unroll
+            for (int j = 0; j < TASKS; ++j) {
+                const int task = ptid + j * NUM_A_THREADS;
+                const int row = task >> 3, ch = task & 7;
+                const float v[8] = {cur[2 * j].x, cur[2 * j].y, cur[2 * j].z, cur[2 * j].w,
+                                    cur[2 * j + 1].x, cur[2 * j + 1].y, cur[2 * j + 1].z, cur[2 * j + 1].w};
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                const uint32_t off = swz(row, ch);
+                *reinterpret_cast<uint4*>(sa_hi + off) = hi;
+                *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+            }
+            fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
+            mbar_arrive(full_bar(stage));
+            if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int j = 0; j < 2 * TASKS; ++j) cur[j] = nxt[j];
+            t = tn; kb = kbn; have = have_next;
+        }
+    } else if (warp >= B_WARP0) {
+        // ================================================================ B loaders (pre-split bf16, cp.async)
+        const int ptid = tid - B_WARP0 * 32;
         int stage = 0;
         uint32_t phase = 0;
         bool ok = true;
         for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-            const int64_t m0 = (t / n_tiles) * BM;
             const int n0 = (int)(t % n_tiles) * BN;
             for (int kb = 0; kb < KB; ++kb) {
                 if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) { ok = false; break; }
-                unsigned char* sa_hi = smem + stage * cfg::STAGE_BYTES;
-                unsigned char* sa_lo = sa_hi + cfg::A_BYTES;
-                unsigned char* sb_hi = sa_lo + cfg::A_BYTES;
-                unsigned char* sb_lo = sb_hi + cfg::B_BYTES;
+                const uint32_t sb_hi = smem_u32(smem + stage * cfg::STAGE_BYTES + 2 * cfg::A_BYTES);
+                const uint32_t sb_lo = sb_hi + cfg::B_BYTES;
                 const int k0 = kb * BK;
-                const bool fullk = vecA && (k0 + BK <= K);
-                // ---- A: 128 rows x 8 chunks of 8 fp32
-#pragma unroll 2
-                for (int task = ptid; task < BM * 8; task += NUM_PROD_THREADS) {
-                    const int row = task >> 3, ch = task & 7;
-                    int64_t gm = m0 + row;
-                    if (gm >= M) gm = M - 1;                   // clamp: rows beyond M are never stored
-                    const float* src = A + gm * lda + k0 + ch * 8;
-                    float v[8];
-                    if (fullk) {
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = (k0 + ch * 8 + j < K) ? __ldg(src + j) : 0.f;
-                    }
-                    uint4 hi, lo;
-                    split8(v, hi, lo);
-                    const uint32_t off = swz(row, ch);
-                    *reinterpret_cast<uint4*>(sa_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(sa_lo + off) = lo;
-                }
-                // ---- B: BN rows x 8 chunks of 8 bf16, both halves (already split and zero padded)
-#pragma unroll 2
-                for (int task = ptid; task < BN * 8; task += NUM_PROD_THREADS) {
+#pragma unroll 8
+                for (int task = ptid; task < BN * 8; task += NUM_B_THREADS) {
                     const int row = task >> 3, ch = task & 7;
                     const size_t e = (size_t)(n0 + row) * Kp + k0 + ch * 8;
-                    const uint4 h = __ldg(reinterpret_cast<const uint4*>(Bhi + e));
-                    const uint4 l = __ldg(reinterpret_cast<const uint4*>(Blo + e));
                     const uint32_t off = swz(row, ch);
-                    *reinterpret_cast<uint4*>(sb_hi + off) = h;
-                    *reinterpret_cast<uint4*>(sb_lo + off) = l;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_hi + off), "l"(Bhi + e) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_lo + off), "l"(Blo + e) : "memory");
                 }
-                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                fence_proxy_async();
                 mbar_arrive(full_bar(stage));
                 if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -269,49 +315,61 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         }
     } else {
         // ================================================================ epilogue (warps 0..3)
+        // TMEM gives each thread one accumulator row; 32x32 blocks go through a padded shared tile so
+        // that global stores are 128-byte contiguous per row (8 lanes x float4).
+        float* T = epi_smem + warp * (32 * EPI_LD);
         int acc = 0;
         uint32_t acc_phase = 0;
         bool ok = true;
         for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-            const int64_t m0 = (t / n_tiles) * BM;
+            const int64_t m0 = (t / n_tiles) * BM + warp * 32;
             const int n0 = (int)(t % n_tiles) * BN;
             if (!mbar_wait(tfull_bar(acc), acc_phase, vstatus)) { ok = false; break; }
             tc_fence_after();
-            const int64_t row = m0 + warp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-            float* crow = C + row * ldc + n0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
                 tmem_ld16(taddr + c0, v);               // all lanes participate (sync.aligned)
-                if (row < M && n0 + c0 < N) {
-                    if (vecC && n0 + c0 + 16 <= N) {
+                tmem_ld16(taddr + c0 + 16, v + 16);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            if (bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + q);
-                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                            }
-                            if (accumulate) {
-                                const float4 old = *reinterpret_cast<const float4*>(crow + c0 + 4 * q);
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
-                            *reinterpret_cast<float4*>(crow + c0 + 4 * q) = o;
-                        }
-                    } else {
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                __syncwarp();
+                if (n0 + c0 < N) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int col = n0 + c0 + j;
-                            if (col < N) {
-                                float o = v[j];
-                                if (bias) o += __ldg(bias + col);
-                                if (accumulate) o += crow[c0 + j];
-                                crow[c0 + j] = o;
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = rr * 4 + (lane >> 3), cq = (lane & 7) * 4;
+                        const int64_t row = m0 + r;
+                        const int col = n0 + c0 + cq;
+                        if (row < M && col < N) {
+                            float4 o = *reinterpret_cast<const float4*>(T + r * EPI_LD + cq);
+                            float* cp = C + row * ldc + col;
+                            if (vecC && col + 4 <= N) {
+                                if (bias) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col));
+                                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                                }
+                                if (accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(cp);
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *reinterpret_cast<float4*>(cp) = o;
+                            } else {
+                                const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (col + j < N) {
+                                        float x = ov[j];
+                                        if (bias) x += __ldg(bias + col + j);
+                                        if (accumulate) x += cp[j];
+                                        cp[j] = x;
+                                    }
                             }
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));

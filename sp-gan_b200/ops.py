@@ -30,8 +30,10 @@ def L():
 # (gradient_penalty.py:31-33, only_inputs=True): parameter gradients are not requested there.
 _INPUT_GRAD_ONLY = False
 
-# engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores where supported
-GEMM_ENGINE = 0
+# engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores (bf16x3 split, fp32 accumulate)
+# wherever the shape allows; override with SPGAN_GEMM_ENGINE=0 for an all-fp32-FMA run.
+import os as _os
+GEMM_ENGINE = int(_os.environ.get("SPGAN_GEMM_ENGINE", "1"))
 
 
 # Set by GradientPenalty around netD(interpolates): the critic then records the unfused,
