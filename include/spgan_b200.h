@@ -87,10 +87,12 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  * Conv2d(1x1) / Conv2d([1,k]) / Linear of Generator.py:56-71,107-135 and
  * Discriminator.py:55-94 and their autograd (dgrad: NN, wgrad: TN with split-K).
  * engine: 0 = fp32 CUDA-core tiles (exact fp32 products, sequential-k accumulation per tile);
- *         1 = tcgen05 tensor cores: operands split into bf16 hi+lo, three MMAs per product term
- *             (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM; ~2^-16 relative per product.
- *             Needs transA == 0, M >= 128, N >= 16, K >= 16 and a workspace of
- *             spgan_gemm_workspace(1, N, K) bytes (256-byte aligned); otherwise engine 0 runs.
+ *         1 = tcgen05 tensor cores, TF32x3: operands split x = hi + lo in tf32, three MMAs per product
+ *             (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM; ~2^-21 relative per product, i.e.
+ *             fp32-faithful.  2 = the same pipeline with a bf16 split (~2^-16 per product, twice the
+ *             MMA rate; opt-in).  Engines 1/2 need transA == 0, M >= 128, N >= 16, K >= 16 and a
+ *             workspace of spgan_gemm_workspace(engine, N, K) bytes (256-byte aligned); otherwise
+ *             engine 0 runs.
  * The first int of the workspace is a status word: non-zero after completion means the kernel
  * aborted on an internal pipeline timeout (never expected; checked by the tests). */
 size_t spgan_gemm_workspace(int engine, int N, int K);

@@ -347,16 +347,17 @@ class TrainState:
             self.d[k].requires_grad_(d_flag)
 
 
-def wgan_gp_train_step(st, x, z_d, z_g, real, alpha, lambda_gp=10.0, gamma=1.0):
+def wgan_gp_train_step(st, x, z_d, z_g, real, alpha, lambda_gp=10.0, gamma=1.0, idx2_d=None, idx2_g=None):
     """One iteration of model.py:239-279 with gan='wgan' and GradientPenalty(lambda_gp) added
     to lossD.  x [B,N,3] sphere, z_* [B,N,nz], real [B,3,N], alpha [B,1,1].
-    Returns python floats {loss_d, gp, loss_g}."""
+    idx2_d / idx2_g optionally pin EdgeConv2's neighbour lists of the two generator forwards
+    (int64 [B, N*k]) for sensitivity studies.  Returns python floats {loss_d, gp, loss_g}."""
     opts = st.opts
     # ---- D phase ----
     st.set_requires_grad(False, True)
     st.opt_d.zero_grad(set_to_none=True)
     real = real.detach().clone().requires_grad_(True)     # model.py:245 (Variable(..., requires_grad=True))
-    fake = generator_forward(st.g, x, z_d, opts, training=True).detach()
+    fake = generator_forward(st.g, x, z_d, opts, training=True, idx2=idx2_d).detach()
     d_real = discriminator_forward(st.d, real, True)
     d_fake = discriminator_forward(st.d, fake, True)
     gp = gradient_penalty(lambda t: discriminator_forward(st.d, t, True), real, fake, alpha, lambda_gp, gamma)
@@ -366,7 +367,7 @@ def wgan_gp_train_step(st, x, z_d, z_g, real, alpha, lambda_gp=10.0, gamma=1.0):
     # ---- G phase ----
     st.set_requires_grad(True, False)
     st.opt_g.zero_grad(set_to_none=True)
-    fake = generator_forward(st.g, x, z_g, opts, training=True)
+    fake = generator_forward(st.g, x, z_g, opts, training=True, idx2=idx2_g)
     _ = discriminator_forward(st.d, real, True)            # model.py:274 (result unused by wgan gen_loss)
     d_fake = discriminator_forward(st.d, fake, True)
     loss_g = gen_loss_wgan(d_fake)

@@ -11,7 +11,7 @@ shapes = [(131072, 1024, 256, "D fc2 fwd"), (131072, 256, 1024, "D fc2 dgrad"), 
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
 for M, N, K, name in shapes:
     A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); out = torch.empty(M, N, device="cuda")
-    for eng in (0, 1):
+    for eng in (0, 1, 2):
         ts = []
         for it in range(5):
             flush.zero_()
@@ -19,6 +19,6 @@ for M, N, K, name in shapes:
             e0.record(); ops.gemm_raw(A, B, None, False, True, out=out, engine=eng); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts)[len(ts) // 2]
-        st = int(ops.LAST_TC_WORKSPACE.view(torch.int32)[0]) if eng == 1 else 0
+        st = int(ops.LAST_TC_WORKSPACE.view(torch.int32)[0]) if eng >= 1 else 0
         print("%-26s M=%8d N=%5d K=%5d engine %d: %8.3f ms  %7.1f TFLOP/s  out %6.0f GB/s  status %d" % (
             name, M, N, K, eng, t, 2.0 * M * N * K / t / 1e9, M * N * 4 / t / 1e6, st))

@@ -232,11 +232,12 @@ int spgan_gemm_simt(int transA, int transB, int64_t M, int N, int K, const float
 
 size_t spgan_gemm_tc_workspace(int N, int K);
 bool spgan_gemm_tc_supported(int transA, int64_t M, int N, int K);
-int spgan_gemm_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
-                  float* C, int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st);
+int spgan_gemm_tc(int mode_bf16, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                  int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, void* workspace,
+                  cudaStream_t st);
 
 extern "C" size_t spgan_gemm_workspace(int engine, int N, int K) {
-    if (engine != 1 || N < 1 || K < 1) return 0;
+    if ((engine != 1 && engine != 2) || N < 1 || K < 1) return 0;
     return spgan_gemm_tc_workspace(N, K);
 }
 
@@ -246,8 +247,9 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
     SPGAN_CHECK_ARG(A && B && C && M >= 0 && N >= 1 && K >= 1);
     SPGAN_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N);
     if (M == 0) return SPGAN_OK;
-    if (engine == 1 && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
+    if ((engine == 1 || engine == 2) && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
         workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
-        return spgan_gemm_tc(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, as_stream(stream));
+        return spgan_gemm_tc(engine == 2, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
+                             as_stream(stream));
     return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream));
 }

@@ -1,8 +1,12 @@
 // tcgen05 GEMM (engine 1 of spgan_gemm): C[M,N] = A[M,K] * B^T (+bias) (+C), fp32 in / fp32 out.
 //
-// Precision: every fp32 operand is split into two bf16 terms (hi = truncation, lo = rn(x - hi)) and
-// the product is formed as Ahi*Bhi + Ahi*Blo + Alo*Bhi on the 5th-gen tensor cores with fp32
-// accumulation in TMEM ("bf16x3", ~2^-16 relative per product; the dropped lo*lo term is 2^-16).
+// Precision: every fp32 operand is split into two narrow terms x = hi + lo and the product is formed
+// as Ahi*Bhi + Ahi*Blo + Alo*Bhi on the 5th-gen tensor cores with fp32 accumulation in TMEM:
+//   TF32 mode (engine 1, default): hi = rna_tf32(x), lo = rna_tf32(x - hi): 22 significant bits,
+//       ~2^-21 relative per product -- indistinguishable from an fp32 FMA chain at K <= 1280;
+//   BF16 mode (engine 2, "fast"): hi = trunc_bf16(x), lo = rn_bf16(x - hi): ~2^-16 per product,
+//       twice the MMA rate; NOT used by default because train-mode BatchNorm and the gradient
+//       penalty amplify it to the 1e-3 parity bar (DESIGN.md "GEMM precision").
 //
 // Structure (one persistent CTA per SM, 15 warps):
 //   warps 0-3   epilogue : tcgen05.ld accumulator rows from TMEM -> shared transpose -> (+bias, +C)
@@ -20,7 +24,7 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;                      // bf16 elements per k-block = one 128-byte swizzle row
+// one k-block = one 128-byte swizzle row per matrix row: 64 bf16 or 32 tf32 elements
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
 constexpr int A_WARP0 = 5;                  // 8 warps convert the fp32 A operand
@@ -31,8 +35,10 @@ constexpr int TC_THREADS = 15 * 32;         // 480
 constexpr int EPI_LD = 36;                  // padded row stride (floats) of the epilogue staging tile
 constexpr uint32_t SPIN_LIMIT = 1u << 20;
 
-template <int BN>
+template <int BN, bool TF32>
 struct Cfg {
+    static constexpr int BK = TF32 ? 32 : 64;            // elements per k-block
+    static constexpr int CHUNK = TF32 ? 4 : 8;           // elements per 16-byte chunk
     static constexpr int A_BYTES = BM * 128;             // one half (hi or lo)
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -86,15 +92,25 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::tf32 (K=8 per instruction) or kind::f16 (bf16, K=16)
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+    if constexpr (TF32) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
@@ -119,9 +135,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor: D=f32 [4,6), A format [7,10), B format [10,13) (1 = bf16, 2 = tf32), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool tf32) {
+    const uint32_t fmt = tf32 ? 2u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t swz(int row, int chunk) {
@@ -143,13 +161,28 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int BN>
+// 4 fp32 -> 4 tf32 "hi" (round to nearest) + 4 tf32 "lo" (rn of the exact remainder)
+__device__ __forceinline__ void split4_tf32(float4 x, uint4& hi, uint4& lo) {
+    const float v[4] = {x.x, x.y, x.z, x.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[i]) : "f"(v[i]));
+        const float r = v[i] - __uint_as_float(h[i]);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[i]) : "f"(r));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
-               const uint16_t* __restrict__ Bhi, const uint16_t* __restrict__ Blo, int Kp, int n_tiles,
+               const unsigned char* __restrict__ Bhi, const unsigned char* __restrict__ Blo, int Kp, int n_tiles,
                float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int accumulate, int* status,
                bool vecA, bool vecC) {
-    using cfg = Cfg<BN>;
+    using cfg = Cfg<BN, TF32>;
+    constexpr int BK = cfg::BK, CHUNK = cfg::CHUNK, ESZ = TF32 ? 4 : 2;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
@@ -188,9 +221,10 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         // Each thread owns 4 (row, 8-float chunk) tasks of a k-block; the loads of the NEXT k-block are
         // issued before the current one is converted, so HBM latency overlaps conversion and the wait
         // for a free stage.
-        constexpr int TASKS = BM * 8 / NUM_A_THREADS;          // 4
+        constexpr int TASKS = BM * 8 / NUM_A_THREADS;          // 4 (row, 16-byte chunk) tasks per thread
+        constexpr int V = TF32 ? 1 : 2;                        // float4 loads per task
         const int ptid = tid - A_WARP0 * 32;
-        float4 cur[2 * TASKS], nxt[2 * TASKS];
+        float4 cur[V * TASKS], nxt[V * TASKS];
         auto load_a = [&](int64_t t, int kb, float4* r) {
             const int64_t m0 = (t / n_tiles) * BM;
             const int k0 = kb * BK;
@@ -201,16 +235,16 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                 const int row = task >> 3, ch = task & 7;
                 int64_t gm = m0 + row;
                 if (gm >= M) gm = M - 1;                       // clamp: rows beyond M are never stored
-                const float* src = A + gm * lda + k0 + ch * 8;
+                const float* src = A + gm * lda + k0 + ch * CHUNK;
                 if (fullk) {
-                    r[2 * j] = __ldg(reinterpret_cast<const float4*>(src));
-                    r[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                } else {
-                    float v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = (k0 + ch * 8 + e < K) ? __ldg(src + e) : 0.f;
-                    r[2 * j] = make_float4(v[0], v[1], v[2], v[3]);
-                    r[2 * j + 1] = make_float4(v[4], v[5], v[6], v[7]);
+                    for (int q = 0; q < V; ++q) r[V * j + q] = __ldg(reinterpret_cast<const float4*>(src) + q);
+                } else {
+                    float v[CHUNK];
+#pragma unroll
+                    for (int e = 0; e < CHUNK; ++e) v[e] = (k0 + ch * CHUNK + e < K) ? __ldg(src + e) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < V; ++q) r[V * j + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
             }
         };
@@ -233,10 +267,14 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
             for (int j = 0; j < TASKS; ++j) {
                 const int task = ptid + j * NUM_A_THREADS;
                 const int row = task >> 3, ch = task & 7;
-                const float v[8] = {cur[2 * j].x, cur[2 * j].y, cur[2 * j].z, cur[2 * j].w,
-                                    cur[2 * j + 1].x, cur[2 * j + 1].y, cur[2 * j + 1].z, cur[2 * j + 1].w};
                 uint4 hi, lo;
-                split8(v, hi, lo);
+                if constexpr (TF32) {
+                    split4_tf32(cur[j], hi, lo);
+                } else {
+                    const float v[8] = {cur[2 * j].x, cur[2 * j].y, cur[2 * j].z, cur[2 * j].w,
+                                        cur[2 * j + 1].x, cur[2 * j + 1].y, cur[2 * j + 1].z, cur[2 * j + 1].w};
+                    split8(v, hi, lo);
+                }
                 const uint32_t off = swz(row, ch);
                 *reinterpret_cast<uint4*>(sa_hi + off) = hi;
                 *reinterpret_cast<uint4*>(sa_lo + off) = lo;
@@ -245,7 +283,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
             mbar_arrive(full_bar(stage));
             if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-            for (int j = 0; j < 2 * TASKS; ++j) cur[j] = nxt[j];
+            for (int j = 0; j < V * TASKS; ++j) cur[j] = nxt[j];
             t = tn; kb = kbn; have = have_next;
         }
     } else if (warp >= B_WARP0) {
@@ -264,7 +302,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
 #pragma unroll 8
                 for (int task = ptid; task < BN * 8; task += NUM_B_THREADS) {
                     const int row = task >> 3, ch = task & 7;
-                    const size_t e = (size_t)(n0 + row) * Kp + k0 + ch * 8;
+                    const size_t e = ((size_t)(n0 + row) * Kp + k0 + ch * CHUNK) * ESZ;      // byte offset
                     const uint32_t off = swz(row, ch);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_hi + off), "l"(Bhi + e) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_lo + off), "l"(Blo + e) : "memory");
@@ -277,7 +315,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         }
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer
-        constexpr uint32_t idesc = make_idesc(BM, BN);
+        constexpr uint32_t idesc = make_idesc(BM, BN, TF32);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         bool ok = true;
@@ -296,11 +334,11 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                     const uint64_t dah = make_desc(sa_hi), dal = make_desc(sa_lo);
                     const uint64_t dbh = make_desc(sb_hi), dbl = make_desc(sb_lo);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        const uint64_t adv = (uint64_t)(kk * 2);          // 32 bytes per K=16 step, >>4
-                        umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-                        umma_bf16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-                        umma_bf16(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+                    for (int kk = 0; kk < 4; ++kk) {                      // 4 MMA k-steps of 32 bytes per row
+                        const uint64_t adv = (uint64_t)(kk * 2);          // 32 bytes >> 4
+                        umma<TF32>(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                        umma<TF32>(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+                        umma<TF32>(tmem_d, dal + adv, dbh + adv, idesc, 1u);
                     }
                     umma_commit(empty_bar(stage));        // frees the stage once the MMAs have read it
                 }
@@ -386,66 +424,88 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     }
 }
 
-// B (weights) -> zero-padded bf16 hi / lo, K-major [Npad, Kp]; also clears the status word
+// B (weights) -> zero-padded hi / lo terms, K-major [Npad, Kp] (bf16 or tf32-in-fp32); clears the status word
+template <bool TF32>
 __global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int transB, int N, int K, int Npad, int Kp,
-                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int* status) {
+                                  void* __restrict__ hi_, void* __restrict__ lo_, int* status) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
     const int64_t total = (int64_t)Npad * Kp;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int n = (int)(i / Kp), k = (int)(i % Kp);
         float v = 0.f;
         if (n < N && k < K) v = transB ? __ldg(B + (int64_t)n * ldb + k) : __ldg(B + (int64_t)k * ldb + n);
-        const uint32_t u = __float_as_uint(v);
-        const float r = v - __uint_as_float(u & 0xffff0000u);
-        uint32_t l2;
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(0.f), "f"(r));
-        hi[i] = (uint16_t)(u >> 16);
-        lo[i] = (uint16_t)(l2 & 0xffffu);
+        if constexpr (TF32) {
+            uint32_t h, l;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+            const float r = v - __uint_as_float(h);
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+            reinterpret_cast<uint32_t*>(hi_)[i] = h;
+            reinterpret_cast<uint32_t*>(lo_)[i] = l;
+        } else {
+            const uint32_t u = __float_as_uint(v);
+            const float r = v - __uint_as_float(u & 0xffff0000u);
+            uint32_t l2;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(0.f), "f"(r));
+            reinterpret_cast<uint16_t*>(hi_)[i] = (uint16_t)(u >> 16);
+            reinterpret_cast<uint16_t*>(lo_)[i] = (uint16_t)(l2 & 0xffffu);
+        }
     }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-template <int BN>
-int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const uint16_t* hi, const uint16_t* lo, int Kp,
-              int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
-    using cfg = Cfg<BN>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES);
+template <int BN, bool TF32>
+int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const unsigned char* hi, const unsigned char* lo,
+              int Kp, int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
+    using cfg = Cfg<BN, TF32>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = Npad / BN;
     const int64_t total = ((M + BM - 1) / BM) * n_tiles;
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
     const bool vecA = (lda % 4 == 0) && aligned16(A);
     const bool vecC = (ldc % 4 == 0) && aligned16(C) && (bias == nullptr || aligned16(bias));
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc, bias,
-                                                                   accumulate, status, vecA, vecC);
+    gemm_tc_kernel<BN, TF32><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc,
+                                                                         bias, accumulate, status, vecA, vecC);
     return spgan_launch_status();
+}
+
+template <bool TF32>
+int run_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+           int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st) {
+    constexpr int BK = TF32 ? 32 : 64;
+    constexpr size_t ESZ = TF32 ? 4 : 2;
+    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const int Npad = (int)align_up((size_t)N, BN), Kp = (int)align_up((size_t)K, BK);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    int* status = reinterpret_cast<int*>(ws);
+    unsigned char* hi = ws + 256;
+    unsigned char* lo = hi + align_up(align_up((size_t)N, 256) * Kp * ESZ, 256);
+    presplit_b_kernel<TF32><<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, Npad, Kp, hi, lo, status);
+    int rc = spgan_launch_status();
+    if (rc != SPGAN_OK) return rc;
+    if (BN == 64) return launch_tc<64, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    if (BN == 128) return launch_tc<128, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    return launch_tc<256, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
 }
 
 }  // namespace
 
+// workspace big enough for either mode: status word + hi + lo, each up to roundup(N,256) x roundup(K,64) fp32
 size_t spgan_gemm_tc_workspace(int N, int K) {
-    const size_t Npad = align_up((size_t)N, 256), Kp = align_up((size_t)K, BK);
-    return 256 + 2 * align_up(Npad * Kp * sizeof(uint16_t), 256);
+    const size_t Npad = align_up((size_t)N, 256), Kp = align_up((size_t)K, 64);
+    return 256 + 2 * align_up(Npad * Kp * sizeof(float), 256);
 }
 
 bool spgan_gemm_tc_supported(int transA, int64_t M, int N, int K) {
     return !transA && M >= 128 && N >= 16 && K >= 16;
 }
 
-int spgan_gemm_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
-                  float* C, int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st) {
-    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    const int Npad = (int)align_up((size_t)N, BN), Kp = (int)align_up((size_t)K, BK);
-    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
-    int* status = reinterpret_cast<int*>(ws);
-    uint16_t* hi = reinterpret_cast<uint16_t*>(ws + 256);
-    uint16_t* lo = reinterpret_cast<uint16_t*>(ws + 256 + align_up(align_up((size_t)N, 256) * Kp * sizeof(uint16_t), 256));
-    presplit_b_kernel<<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, Npad, Kp, hi, lo, status);
-    int rc = spgan_launch_status();
-    if (rc != SPGAN_OK) return rc;
-    if (BN == 64) return launch_tc<64>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
-    if (BN == 128) return launch_tc<128>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
-    return launch_tc<256>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+int spgan_gemm_tc(int mode_bf16, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                  int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, void* workspace,
+                  cudaStream_t st) {
+    if (mode_bf16) return run_tc<false>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
+    return run_tc<true>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
 }

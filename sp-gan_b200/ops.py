@@ -30,8 +30,9 @@ def L():
 # (gradient_penalty.py:31-33, only_inputs=True): parameter gradients are not requested there.
 _INPUT_GRAD_ONLY = False
 
-# engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores (bf16x3 split, fp32 accumulate)
-# wherever the shape allows; override with SPGAN_GEMM_ENGINE=0 for an all-fp32-FMA run.
+# engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores with the fp32-faithful TF32x3
+# split wherever the shape allows (default), 2 = tcgen05 with the faster bf16x3 split (~2^-16/product).
+# Override with SPGAN_GEMM_ENGINE.
 import os as _os
 GEMM_ENGINE = int(_os.environ.get("SPGAN_GEMM_ENGINE", "1"))
 
@@ -152,8 +153,8 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
         bias = _c(bias)
     engine = GEMM_ENGINE if engine is None else engine
     ws, ws_bytes = None, 0
-    if engine == 1 and not ta and M >= 128 and N >= 16 and K >= 16:
-        ws_bytes = L().gemm_workspace(1, N, K)
+    if engine in (1, 2) and not ta and M >= 128 and N >= 16 and K >= 16:
+        ws_bytes = L().gemm_workspace(engine, N, K)
         ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
         LAST_TC_WORKSPACE = ws
     L().gemm(int(ta), int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),

@@ -90,6 +90,63 @@ def noise_floor_generator(g_sd, o, xg, zg, rg, idx1, idx2, arrs):
     return res
 
 
+def _perturbed(sd, rel, seed):
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for k, v in sd.items():
+        if v.is_floating_point() and "running_" not in k:
+            out[k] = v * (1.0 + rel * torch.from_numpy(rng.standard_normal(tuple(v.shape)).astype(np.float32)))
+        else:
+            out[k] = v.clone()
+    return out
+
+
+def sensitivity_generator(g_sd, o, xg, zg, rg, idx1, idx2, rel=1e-6):
+    """Conditioning of the reference path itself: relative L2 change of every parameter gradient when
+    ALL weights are perturbed by `rel` (1e-6, i.e. ~16 fp32 ulps) with the neighbour lists held fixed.
+    LeakyReLU(0.01) masks and max-pool arg-maxes flip under such perturbations, so this is far above
+    `rel`; parity tests accept max(1e-3, 3 x this) per tensor (DESIGN.md "Parity")."""
+    def grads(sd):
+        leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v.clone())
+                for k, v in sd.items()}
+        out = R.generator_forward(leaf, xg, zg, o, training=True, idx1=idx1, idx2=idx2)
+        (out * rg).sum().backward()
+        return {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
+    g0 = grads(g_sd)
+    res = {}
+    for seed in (101, 102):
+        g1 = grads(_perturbed(g_sd, rel, seed))
+        for k in g0:
+            d = float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-30))
+            res["sens.grad." + k] = np.float32(max(d, float(res.get("sens.grad." + k, 0.0))))
+    return res
+
+
+def sensitivity_train_step(o, xg, arrs, Nt, rel=1e-6):
+    """Same for the first composed train step: D-phase gradients of D, G-phase gradients of G."""
+    tile = lambda a: torch.from_numpy(np.tile(a, (1, Nt, 1)))
+    i2d = torch.from_numpy(arrs["s0.idx2_d"].astype(np.int64)).reshape(xg.shape[0], -1)
+    i2g = torch.from_numpy(arrs["s0.idx2_g"].astype(np.int64)).reshape(xg.shape[0], -1)
+
+    def grads(gs, ds):
+        st = R.TrainState(gs, ds, o)
+        R.wgan_gp_train_step(st, xg, tile(arrs["s0.z_d"]), tile(arrs["s0.z_g"]),
+                             torch.from_numpy(arrs["s0.data"]).transpose(2, 1), torch.from_numpy(arrs["s0.alpha"]),
+                             idx2_d=i2d, idx2_g=i2g)
+        return ({k: st.d[k].grad for k in st.d_params if st.d[k].grad is not None},
+                {k: st.g[k].grad for k in st.g_params if st.g[k].grad is not None})
+    gs, ds = R.synth_state(R.generator_spec(o), 61), R.synth_state(R.discriminator_spec(o), 62)
+    d0, g0 = grads(gs, ds)
+    res = {}
+    for seed in (201, 202):
+        d1, g1 = grads(_perturbed(gs, rel, seed), _perturbed(ds, rel, seed + 10))
+        for pre, a, b in (("sens.s0.gradD.", d0, d1), ("sens.s0.gradG.", g0, g1)):
+            for k in a:
+                dd = float((b[k] - a[k]).norm() / (a[k].norm() + 1e-30))
+                res[pre + k] = np.float32(max(dd, float(res.get(pre + k, 0.0))))
+    return res
+
+
 def sphere(n):
     ball = np.loadtxt(os.path.join(REF, "template/balls/%d.xyz" % n))[:, :3]
     return R.normalize_cloud(ball)       # model.py:46-52 restated
@@ -238,6 +295,7 @@ def main():
             arrs.update(grads_of(G))
             arrs.update(buffers_of(G))
             arrs.update(noise_floor_generator(g_sd, o, xg, zg, rg, idx1, idx2, arrs))
+            arrs.update(sensitivity_generator(g_sd, o, xg, zg, rg, idx1, idx2))
             G.eval()
             with torch.no_grad():
                 arrs["out_eval"] = G(xg, zg).numpy()
@@ -309,6 +367,7 @@ def main():
         arrs["s%d.loss_g" % step] = np.float32(lossG.item())
         print("train step", step, lossD.item(), gp.item(), lossG.item())
     hook.remove()
+    arrs.update(sensitivity_train_step(o, xg, arrs, Nt))
     arrs.update(buffers_of(G, "end.bufG."))
     arrs.update(buffers_of(D, "end.bufD."))
     arrs.update({"end.G." + k: pack(p) for k, p in G.named_parameters()})

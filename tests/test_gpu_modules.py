@@ -24,7 +24,10 @@ def _load(module, spec, seed):
 
 
 def _check_grads(module, g, prefix="grad.", tol=TOL, max_tol=None):
-    """Per-parameter relative check.  Gradients that are mathematically zero (a conv bias feeding a
+    """Per-parameter relative check.  Where the golden file carries `sens.<key>` -- the relative change
+    of the REFERENCE's own gradient under a 1e-6 relative perturbation of the weights (LeakyReLU masks
+    and max-pool arg-maxes flip; measured by tests/golden/make_golden.py) -- the bar for that tensor is
+    max(tol, 3 x sens): parity cannot be tighter than the reference's own conditioning.  Gradients that are mathematically zero (a conv bias feeding a
     train-mode BatchNorm) are rounding noise in the reference too (~1e-6 of the layer's scale): they
     are compared against the largest gradient magnitude of the module instead of their own."""
     from conftest import pack_like_golden, rel_err
@@ -40,7 +43,8 @@ def _check_grads(module, g, prefix="grad.", tol=TOL, max_tol=None):
             got = pack_like_golden(p.grad)
             assert float(np.abs(got - ref).max()) <= tol * 1e-2 * scale, (k, "noise-level gradient too large")
         else:
-            assert_rel(p.grad, ref, tol, prefix + k, max_tol=max_tol)
+            t = min(max(tol, 3.0 * float(g.get("sens." + prefix + k, 0.0))), 0.25)
+            assert_rel(p.grad, ref, t, prefix + k, max_tol=max(10 * t, max_tol or 0.0))
         n += 1
     assert n > 0
 
@@ -158,7 +162,7 @@ def test_generator(tag, kw, sphere256):
     if tag != "default":
         return
     _scalar_loss(out, torch.from_numpy(g["r"]).cuda()).backward()
-    _check_grads(G, g, max_tol=10 * TOL)
+    _check_grads(G, g)
     _check_bufs(G, g)
     # free-running kNN on our own features: flips only at near ties
     G.debug_idx = None
@@ -228,11 +232,11 @@ def test_train_step_against_reference_golden(sphere256):
         G.debug_idx = (None, torch.from_numpy(g["s%d.idx2_d" % step].astype(np.int32)).cuda())
         loss_d, gp = tr.d_phase(x, tile(g["s%d.z_d" % step]), real, alpha)
         if step == 0:
-            _check_grads(D, g, "s0.gradD.", tol=2e-3, max_tol=2e-2)
+            _check_grads(D, g, "s0.gradD.")
         G.debug_idx = (None, torch.from_numpy(g["s%d.idx2_g" % step].astype(np.int32)).cuda())
         loss_g = tr.g_phase(x, tile(g["s%d.z_g" % step]), real)
         if step == 0:
-            _check_grads(G, g, "s0.gradG.", tol=5e-3, max_tol=5e-2)
+            _check_grads(G, g, "s0.gradG.")
         for key, val in (("loss_d", loss_d), ("gp", gp), ("loss_g", loss_g)):
             ref = float(g["s%d.%s" % (step, key)])
             # step 0 is a pure forward of the initial weights.  Step 1 follows one Adam update whose very first
