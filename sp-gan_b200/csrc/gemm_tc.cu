@@ -43,7 +43,11 @@ struct Cfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
-    static constexpr int TMEM_COLS = 2 * BN;             // 128 / 256 / 512: powers of two
+    // TF32 mode keeps the small cross terms (hi*lo + lo*hi) in a second accumulator: the tensor core adds
+    // into TMEM with truncation, so the error grows with the number of accumulations into the LARGE sum;
+    // this cuts that count by 3 (measured: rms error ~7e-9*K -> ~2.4e-9*K).
+    static constexpr int NACC = TF32 ? 2 : 1;
+    static constexpr int TMEM_COLS = 2 * NACC * BN;      // two tile buffers; power of two <= 512
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                       NUM_EPI_WARPS * 32 * 36 * 4 /*epilogue staging*/;
 };
@@ -322,7 +326,8 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
             if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1, vstatus)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * cfg::NACC * BN);
+            const uint32_t tmem_x = TF32 ? tmem_d + BN : tmem_d;          // cross-term accumulator
             for (int kb = 0; kb < KB; ++kb) {
                 if (!mbar_wait(full_bar(stage), phase, vstatus)) { ok = false; break; }
                 tc_fence_after();
@@ -336,9 +341,10 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {                      // 4 MMA k-steps of 32 bytes per row
                         const uint64_t adv = (uint64_t)(kk * 2);          // 32 bytes >> 4
-                        umma<TF32>(tmem_d, dah + adv, dbh + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-                        umma<TF32>(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-                        umma<TF32>(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+                        const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+                        umma<TF32>(tmem_d, dah + adv, dbh + adv, idesc, first);
+                        umma<TF32>(tmem_x, dah + adv, dbl + adv, idesc, TF32 ? first : 1u);
+                        umma<TF32>(tmem_x, dal + adv, dbh + adv, idesc, 1u);
                     }
                     umma_commit(empty_bar(stage));        // frees the stage once the MMAs have read it
                 }
@@ -364,12 +370,19 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
             const int n0 = (int)(t % n_tiles) * BN;
             if (!mbar_wait(tfull_bar(acc), acc_phase, vstatus)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * cfg::NACC * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
                 tmem_ld16(taddr + c0, v);               // all lanes participate (sync.aligned)
                 tmem_ld16(taddr + c0 + 16, v + 16);
+                if constexpr (TF32) {                   // add the cross-term accumulator
+                    float w[32];
+                    tmem_ld16(taddr + BN + c0, w);
+                    tmem_ld16(taddr + BN + c0 + 16, w + 16);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += w[j];
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                     *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -477,7 +490,7 @@ int run_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, con
            int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st) {
     constexpr int BK = TF32 ? 32 : 64;
     constexpr size_t ESZ = TF32 ? 4 : 2;
-    const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const int BN = N <= 64 ? 64 : ((N <= 128 || TF32) ? 128 : 256);     // TF32: two accumulators per tile
     const int Npad = (int)align_up((size_t)N, BN), Kp = (int)align_up((size_t)K, BK);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
@@ -488,7 +501,9 @@ int run_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, con
     if (rc != SPGAN_OK) return rc;
     if (BN == 64) return launch_tc<64, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
     if (BN == 128) return launch_tc<128, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
-    return launch_tc<256, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    if constexpr (!TF32)
+        return launch_tc<256, false>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    return SPGAN_E_UNSUPPORTED;
 }
 
 }  // namespace

@@ -114,11 +114,13 @@ def sensitivity_generator(g_sd, o, xg, zg, rg, idx1, idx2, rel=1e-6):
         return {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
     g0 = grads(g_sd)
     res = {}
-    for seed in (101, 102):
+    for seed in (101, 102, 103, 104):
         g1 = grads(_perturbed(g_sd, rel, seed))
         for k in g0:
             d = float((g1[k] - g0[k]).norm() / (g0[k].norm() + 1e-30))
             res["sens.grad." + k] = np.float32(max(d, float(res.get("sens.grad." + k, 0.0))))
+    vals = sorted(float(v) for v in res.values() if float(v) < 0.5)
+    res["sens.global"] = np.float32(vals[len(vals) // 2])          # median over tensors of the worst draw
     return res
 
 
@@ -138,12 +140,14 @@ def sensitivity_train_step(o, xg, arrs, Nt, rel=1e-6):
     gs, ds = R.synth_state(R.generator_spec(o), 61), R.synth_state(R.discriminator_spec(o), 62)
     d0, g0 = grads(gs, ds)
     res = {}
-    for seed in (201, 202):
+    for seed in (201, 202, 203, 204):
         d1, g1 = grads(_perturbed(gs, rel, seed), _perturbed(ds, rel, seed + 10))
         for pre, a, b in (("sens.s0.gradD.", d0, d1), ("sens.s0.gradG.", g0, g1)):
             for k in a:
                 dd = float((b[k] - a[k]).norm() / (a[k].norm() + 1e-30))
                 res[pre + k] = np.float32(max(dd, float(res.get(pre + k, 0.0))))
+    vals = sorted(float(v) for v in res.values() if float(v) < 0.5)
+    res["sens.global"] = np.float32(vals[len(vals) // 2])
     return res
 
 
