@@ -247,6 +247,18 @@ def main():
             if name == "spgan_gemm":
                 a[2] += gemm_flops(ia)
         total = sum(a[0] for a in agg.values())
+        if os.environ.get("SPGAN_BENCH_GEMM_TABLE") == "1":        # diagnostic: GEMM time by shape (stderr)
+            byshape = {}
+            for name, ia, s_, e_ in prof:
+                if name == "spgan_gemm":
+                    key = ("T" if ia[0] else "N") + ("T" if ia[1] else "N") + " M=%d N=%d K=%d" % (ia[2], ia[3], ia[4])
+                    b = byshape.setdefault(key, [0.0, 0])
+                    b[0] += s_.elapsed_time(e_)
+                    b[1] += 1
+            for key, b in sorted(byshape.items(), key=lambda kv: -kv[1][0])[:25]:
+                sys.stderr.write("%-40s x%-3d %8.3f ms  %6.1f TFLOP/s\n" % (
+                    key, b[1], b[0], 2.0 * eval(key.split("M=")[1].split()[0]) * eval(key.split("N=")[1].split()[0]) *
+                    eval(key.split("K=")[1]) * b[1] / b[0] / 1e9))
         kernel_share = {k[len("spgan_"):]: round(a[0] / total, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
         peaks = {}
         try:

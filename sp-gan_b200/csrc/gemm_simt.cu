@@ -187,12 +187,13 @@ int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float
                 int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st) {
     const int64_t mt = ceil_div64(M, BM);
     const int nt = (N + BN - 1) / BN;
-    // split-K when the output grid cannot fill the machine and K is long (wgrad: K = #points)
+    // split-K when the output grid cannot fill the machine: wgrad (K = #points) and the critic's
+    // small-batch MLP (M = B rows, K up to 1024) are otherwise a handful of CTAs walking K serially
     int64_t splits = 1;
     const int64_t tiles = mt * nt;
-    if (tiles < 2 * kNumSMs && K >= 2048) {
+    if (tiles < 2 * kNumSMs && K >= 256) {
         splits = (4 * kNumSMs + tiles - 1) / tiles;
-        const int64_t max_splits = K / 512;
+        const int64_t max_splits = K >= 2048 ? K / 512 : K / 64;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
         if (splits > 65535) splits = 65535;
@@ -236,6 +237,11 @@ int spgan_gemm_tc(int mode_bf16, int transB, int64_t M, int N, int K, const floa
                   int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, void* workspace,
                   cudaStream_t st);
 
+bool spgan_gemm_tc_tn_supported(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B,
+                                int64_t ldb);
+int spgan_gemm_tc_tn(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                     int64_t ldc, int accumulate, void* workspace, cudaStream_t st);
+
 extern "C" size_t spgan_gemm_workspace(int engine, int N, int K) {
     if ((engine != 1 && engine != 2) || N < 1 || K < 1) return 0;
     return spgan_gemm_tc_workspace(N, K);
@@ -251,5 +257,10 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
         workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
         return spgan_gemm_tc(engine == 2, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
                              as_stream(stream));
+    // weight gradients: C[M,N] = A^T B with A [K,M], B [K,N], K = #points (TF32x3 for both tensor engines)
+    if ((engine == 1 || engine == 2) && workspace != nullptr && workspace_bytes >= 256 && transA && !transB &&
+        bias == nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+        spgan_gemm_tc_tn_supported(M, N, K, A, lda, B, ldb))
+        return spgan_gemm_tc_tn(M, N, K, A, lda, B, ldb, C, ldc, accumulate, workspace, as_stream(stream));
     return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream));
 }

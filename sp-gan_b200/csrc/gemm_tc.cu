@@ -20,6 +20,7 @@
 // (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
 // Every mbarrier wait is bounded; on timeout the kernel raises a status word instead of hanging.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -33,7 +34,6 @@ constexpr int B_WARP0 = 13;                 // 2 warps stream the pre-split bf16
 constexpr int NUM_B_THREADS = 2 * 32;
 constexpr int TC_THREADS = 15 * 32;         // 480
 constexpr int EPI_LD = 36;                  // padded row stride (floats) of the epilogue staging tile
-constexpr uint32_t SPIN_LIMIT = 1u << 20;
 
 template <int BN, bool TF32>
 struct Cfg {
@@ -52,82 +52,7 @@ struct Cfg {
                                       NUM_EPI_WARPS * 32 * 36 * 4 /*epilogue staging*/;
 };
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait: returns false if the kernel must abort (deadlock guard; sets *status)
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* status) {
-    for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
-        if (mbar_try_wait(bar, parity)) return true;
-        if ((it & 0xfff) == 0xfff && *status != 0) return false;
-    }
-    atomicExch((int*)status, 1);
-    return false;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::tf32 (K=8 per instruction) or kind::f16 (bf16, K=16)
-template <bool TF32>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                     uint32_t accumulate) {
-    if constexpr (TF32) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace tc;
 
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -160,20 +85,6 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
         const float r0 = v[2 * i] - __uint_as_float(u0 & 0xffff0000u);
         const float r1 = v[2 * i + 1] - __uint_as_float(u1 & 0xffff0000u);
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-// 4 fp32 -> 4 tf32 "hi" (round to nearest) + 4 tf32 "lo" (rn of the exact remainder)
-__device__ __forceinline__ void split4_tf32(float4 x, uint4& hi, uint4& lo) {
-    const float v[4] = {x.x, x.y, x.z, x.w};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[i]) : "f"(v[i]));
-        const float r = v[i] - __uint_as_float(h[i]);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[i]) : "f"(r));
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);

@@ -88,3 +88,32 @@ def test_small_shapes_fall_back_to_cuda_cores():
     out = ops.gemm_raw(A, B, None, False, True, engine=1)
     assert ops.LAST_TC_WORKSPACE is None
     assert max(rel_err(out.cpu().numpy(), (A.cpu().double() @ B.cpu().double().t()).numpy())) < 1e-5
+
+
+@pytest.mark.parametrize("Mo,No,K", [(128, 64, 8192), (1024, 256, 20000), (64, 128, 4096), (256, 128, 131072),
+                                     (64, 32, 50000), (128, 1280, 10240), (72, 20, 9001)])
+def test_tc_wgrad_tn_matches_fp64(Mo, No, K):
+    """Weight-gradient form C = A^T B (A [K,Mo], B [K,No]) on the tensor cores (MN-major operands,
+    atomic flush per 1024-row chunk)."""
+    ops = _ops()
+    A, B = _rnd(K, Mo, seed=11), _rnd(K, No, seed=12)
+    ops.LAST_TC_WORKSPACE = None
+    out = ops.gemm_raw(A.cuda(), B.cuda(), None, True, False, engine=1)
+    assert _status(ops) == 0, "tcgen05 pipeline timed out"
+    ref = A.double().t() @ B.double()
+    emax, el2 = rel_err(out.cpu().numpy(), ref.numpy())
+    assert emax < 1e-5 and el2 < 1e-5, (emax, el2)
+    out2 = ops.gemm_raw(A.cuda(), B.cuda(), None, True, False, out=out, accumulate=True, engine=1)
+    assert _status(ops) == 0
+    emax, el2 = rel_err(out2.cpu().numpy(), (2 * ref).numpy())
+    assert emax < 1e-5 and el2 < 1e-5, (emax, el2)
+
+
+def test_tc_wgrad_strided_operands():
+    ops = _ops()
+    G = _rnd(8192, 96, seed=13).cuda()[:, 16:80]        # lda = 96
+    X = _rnd(8192, 160, seed=14).cuda()[:, 32:160]      # ldb = 160
+    out = ops.gemm_raw(G, X, None, True, False, engine=1)
+    assert _status(ops) == 0
+    ref = G.cpu().double().t() @ X.cpu().double()
+    assert max(rel_err(out.cpu().numpy(), ref.numpy())) < 1e-5
