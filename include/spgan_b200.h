@@ -91,8 +91,8 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  *             (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM; ~2^-21 relative per product, i.e.
  *             fp32-faithful.  2 = the same pipeline with a bf16 split (~2^-16 per product, twice the
  *             MMA rate; opt-in).  Engines 1/2 cover transA == 0 with M >= 128, N >= 16, K >= 16 and the
- *             weight-gradient form transA == 1, transB == 0 with K >= 4096, M, N >= 16 and 16-byte
- *             aligned, 4-element-multiple operands (flushed with fp32 atomics every 1024 rows of K);
+ *             weight-gradient form transA == 1, transB == 0 with K >= 4096 and M, N >= 16 (accumulated
+ *             in TMEM per 1024 rows of K and flushed into C with fp32 atomics);
  *             both need a workspace of spgan_gemm_workspace(engine, N, K) bytes (256-byte aligned).
  *             Anything else runs on engine 0.
  * The first int of the workspace is a status word: non-zero after completion means the kernel

@@ -1,9 +1,10 @@
 // tcgen05 weight-gradient GEMM: C[Mo,No] (+)= A^T B with A = dY [K, Mo], B = X [K, No] row-major fp32,
 // K = number of points / edges (1e5 .. 1e6), Mo/No = channel counts.  TF32x3 split like gemm_tc.cu.
 //
-// Both operands are contiguous along their M / N dimension, so the shared tiles use the MN-major
-// canonical layout (128-byte swizzle atoms of 8 k-rows x 32 elements): a global row segment of 32
-// floats becomes one swizzled 128-byte shared row -- fully coalesced loads, 16-byte stores, no transpose.
+// Both operands are contiguous along their M / N dimension while the tensor core wants K-major tiles.
+// The producers transpose on the fly: lane = output channel, each thread gathers 4 consecutive k for its
+// channel with four warp-coalesced 128-byte loads and writes them as ONE 16-byte chunk of the channel's
+// 128-byte swizzled K-major row (conflict-free), so the proven K-major descriptors of gemm_tc.cu apply.
 //
 // Work unit = (output tile 128 x BN, chunk of KC = 1024 rows).  A unit accumulates 32 k-blocks in TMEM and
 // is flushed with fp32 vector atomics into C, which bounds the truncating tensor-core accumulation chain
@@ -34,27 +35,22 @@ struct CfgTN {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + NUM_EPI_WARPS * 32 * EPI_LD * 4;
 };
 
-// MN-major, 128-byte swizzle: LBO = stride between 32-element blocks along M/N (1024 B),
-// SBO = stride between groups of 8 k-rows
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
+// K-major, 128-byte swizzle (same as gemm_tc.cu): rows of 32 tf32, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
 }
-// D=f32, A=B=tf32, both MN-major (bits 15, 16)
-__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
+// D=f32, A=B=tf32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_k(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-
-// byte offset of the 16-byte chunk `c` (4 elements) of k-row `kr` inside a [4 k-groups][NB blocks][8][128 B] tile
-template <int NB>
-__device__ __forceinline__ uint32_t mn_off(int kr, int c) {
-    return (uint32_t)((kr >> 3) * (NB * 1024) + (c >> 3) * 1024 + (kr & 7) * 128 + (((c & 7) ^ (kr & 7)) << 4));
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
 template <int BN>
@@ -63,8 +59,8 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
                   int64_t ldb, float* __restrict__ C, int64_t ldc, int m_tiles, int n_tiles, int64_t k_chunks,
                   int* status, bool vecC) {
     using cfg = CfgTN<BN>;
-    constexpr int A_TASKS = BK * (BM / 4) / NUM_P_THREADS;     // 4
-    constexpr int B_TASKS = BK * (BN / 4) / NUM_P_THREADS;     // 2 / 4 / 8
+    constexpr int A_TASKS = BM * (BK / 4) / NUM_P_THREADS;     // 4 (row, 4-k chunk) tasks per thread
+    constexpr int B_TASKS = BN * (BK / 4) / NUM_P_THREADS;     // 2 / 4 / 8
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
@@ -107,24 +103,29 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
         // ================================================================ producers: both operands
         const int ptid = tid - P_WARP0 * 32;
         float4 cur[A_TASKS + B_TASKS], nxt[A_TASKS + B_TASKS];
+        // task -> (channel row, 16-byte chunk = 4 consecutive k): lanes walk channels => coalesced rows
         auto load_kb = [&](int m0, int n0, int64_t k0, float4* r) {
 #pragma unroll
             for (int j = 0; j < A_TASKS; ++j) {
                 const int task = ptid + j * NUM_P_THREADS;
-                const int kr = task >> 5, c = task & 31;             // 32 chunks of 4 floats per k-row
-                const int m = m0 + c * 4;
-                const int64_t k = k0 + kr;
-                r[j] = (k < K && m + 4 <= Mo) ? __ldg(reinterpret_cast<const float4*>(A + k * lda + m))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int row = task & (BM - 1), c = task / BM;
+                const int m = m0 + row;
+                const int64_t k = k0 + c * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (m < Mo && k + e < K) ? __ldg(A + (k + e) * lda + m) : 0.f;
+                r[j] = make_float4(v[0], v[1], v[2], v[3]);
             }
 #pragma unroll
             for (int j = 0; j < B_TASKS; ++j) {
                 const int task = ptid + j * NUM_P_THREADS;
-                const int kr = task / (BN / 4), c = task % (BN / 4);
-                const int n = n0 + c * 4;
-                const int64_t k = k0 + kr;
-                r[A_TASKS + j] = (k < K && n + 4 <= No) ? __ldg(reinterpret_cast<const float4*>(B + k * ldb + n))
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int row = task % BN, c = task / BN;
+                const int n = n0 + row;
+                const int64_t k = k0 + c * 4;
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = (n < No && k + e < K) ? __ldg(B + (k + e) * ldb + n) : 0.f;
+                r[A_TASKS + j] = make_float4(v[0], v[1], v[2], v[3]);
             }
         };
         int stage = 0;
@@ -150,7 +151,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
                 const int task = ptid + j * NUM_P_THREADS;
                 uint4 hi, lo;
                 split4_tf32(cur[j], hi, lo);
-                const uint32_t off = mn_off<BM / 32>(task >> 5, task & 31);
+                const uint32_t off = swz(task & (BM - 1), task / BM);
                 *reinterpret_cast<uint4*>(sa_hi + off) = hi;
                 *reinterpret_cast<uint4*>(sa_lo + off) = lo;
             }
@@ -159,7 +160,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
                 const int task = ptid + j * NUM_P_THREADS;
                 uint4 hi, lo;
                 split4_tf32(cur[A_TASKS + j], hi, lo);
-                const uint32_t off = mn_off<BN / 32>(task / (BN / 4), task % (BN / 4));
+                const uint32_t off = swz(task % BN, task / BN);
                 *reinterpret_cast<uint4*>(sb_hi + off) = hi;
                 *reinterpret_cast<uint4*>(sb_lo + off) = lo;
             }
@@ -172,8 +173,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
         }
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer
-        constexpr uint32_t idesc = make_idesc_mn(BM, BN);
-        constexpr uint32_t SBO_A = (BM / 32) * 1024, SBO_B = (BN / 32) * 1024;
+        constexpr uint32_t idesc = make_idesc_k(BM, BN);
         int stage = 0;
         uint32_t phase = 0, tphase = 0;
         bool ok = true;
@@ -191,16 +191,15 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
                     const uint32_t sa_lo = sa_hi + cfg::A_BYTES;
                     const uint32_t sb_hi = sa_lo + cfg::A_BYTES;
                     const uint32_t sb_lo = sb_hi + cfg::B_BYTES;
+                    const uint64_t dah = make_desc_k(sa_hi), dal = make_desc_k(sa_lo);
+                    const uint64_t dbh = make_desc_k(sb_hi), dbl = make_desc_k(sb_lo);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {               // one 8-row swizzle atom per MMA k-step
-                        const uint64_t dah = make_desc_mn(sa_hi + kk * SBO_A, SBO_A);
-                        const uint64_t dal = make_desc_mn(sa_lo + kk * SBO_A, SBO_A);
-                        const uint64_t dbh = make_desc_mn(sb_hi + kk * SBO_B, SBO_B);
-                        const uint64_t dbl = make_desc_mn(sb_lo + kk * SBO_B, SBO_B);
+                    for (int kk = 0; kk < BK / 8; ++kk) {               // 32 bytes per K=8 step
+                        const uint64_t adv = (uint64_t)(kk * 2);
                         const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
-                        umma<true>(tmem_d, dah, dbh, idesc, first);
-                        umma<true>(tmem_x, dah, dbl, idesc, first);
-                        umma<true>(tmem_x, dal, dbh, idesc, 1u);
+                        umma<true>(tmem_d, dah + adv, dbh + adv, idesc, first);
+                        umma<true>(tmem_x, dah + adv, dbl + adv, idesc, first);
+                        umma<true>(tmem_x, dal + adv, dbh + adv, idesc, 1u);
                     }
                     umma_commit(empty_bar(stage));
                 }
@@ -296,8 +295,9 @@ int launch_tn(int Mo, int No, int64_t K, const float* A, int64_t lda, const floa
 
 bool spgan_gemm_tc_tn_supported(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B,
                                 int64_t ldb) {
-    return Mo >= 16 && Mo <= 65536 && No >= 16 && K >= 4096 && Mo % 4 == 0 && No % 4 == 0 && lda % 4 == 0 &&
-           ldb % 4 == 0 && aligned16(A) && aligned16(B);
+    (void)A; (void)B; (void)lda; (void)ldb;          // scalar (warp-coalesced) operand loads: no alignment needs
+    // measured: wins over the split-K CUDA-core kernel once the output tile work is large enough
+    return Mo >= 16 && Mo <= 65536 && No >= 16 && K >= 4096 && (int64_t)Mo * No >= 32768;
 }
 
 // C[Mo,No] (+)= A^T B.  workspace: >= 256 bytes (status word).

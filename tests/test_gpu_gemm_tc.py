@@ -90,8 +90,8 @@ def test_small_shapes_fall_back_to_cuda_cores():
     assert max(rel_err(out.cpu().numpy(), (A.cpu().double() @ B.cpu().double().t()).numpy())) < 1e-5
 
 
-@pytest.mark.parametrize("Mo,No,K", [(128, 64, 8192), (1024, 256, 20000), (64, 128, 4096), (256, 128, 131072),
-                                     (64, 32, 50000), (128, 1280, 10240), (72, 20, 9001)])
+@pytest.mark.parametrize("Mo,No,K", [(128, 256, 8192), (1024, 256, 20000), (256, 128, 4096), (256, 128, 131072),
+                                     (64, 512, 50000), (128, 1280, 10240), (72, 500, 9001), (64, 32, 50000)])
 def test_tc_wgrad_tn_matches_fp64(Mo, No, K):
     """Weight-gradient form C = A^T B (A [K,Mo], B [K,No]) on the tensor cores (MN-major operands,
     atomic flush per 1024-row chunk)."""
@@ -111,7 +111,7 @@ def test_tc_wgrad_tn_matches_fp64(Mo, No, K):
 
 def test_tc_wgrad_strided_operands():
     ops = _ops()
-    G = _rnd(8192, 96, seed=13).cuda()[:, 16:80]        # lda = 96
+    G = _rnd(8192, 300, seed=13).cuda()[:, 17:273]      # lda = 300, unaligned start
     X = _rnd(8192, 160, seed=14).cuda()[:, 32:160]      # ldb = 160
     out = ops.gemm_raw(G, X, None, True, False, engine=1)
     assert _status(ops) == 0
