@@ -187,13 +187,14 @@ int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float
                 int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st) {
     const int64_t mt = ceil_div64(M, BM);
     const int nt = (N + BN - 1) / BN;
-    // split-K when the output grid cannot fill the machine: wgrad (K = #points) and the critic's
-    // small-batch MLP (M = B rows, K up to 1024) are otherwise a handful of CTAs walking K serially
+    // split-K (fp32 atomics) when the output grid cannot fill the machine and K is long: weight gradients,
+    // K = #points.  Forward-path shapes (K <= 1280) never split, so forward results are run-to-run
+    // deterministic.
     int64_t splits = 1;
     const int64_t tiles = mt * nt;
-    if (tiles < 2 * kNumSMs && K >= 256) {
+    if (tiles < 2 * kNumSMs && K >= 2048) {
         splits = (4 * kNumSMs + tiles - 1) / tiles;
-        const int64_t max_splits = K >= 2048 ? K / 512 : K / 64;
+        const int64_t max_splits = K / 512;
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
         if (splits > 65535) splits = 65535;
