@@ -259,7 +259,8 @@ def main():
                 sys.stderr.write("%-40s x%-3d %8.3f ms  %6.1f TFLOP/s\n" % (
                     key, b[1], b[0], 2.0 * eval(key.split("M=")[1].split()[0]) * eval(key.split("N=")[1].split()[0]) *
                     eval(key.split("K=")[1]) * b[1] / b[0] / 1e9))
-        kernel_share = {k[len("spgan_"):]: round(a[0] / total, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
+        kernel_share = {k[len("spgan_"):]: round(a[0] / total, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+        kernel_share["_sum_of_kernel_ms"] = round(total, 3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -8,14 +8,14 @@
 //       twice the MMA rate; NOT used by default because train-mode BatchNorm and the gradient
 //       penalty amplify it to the 1e-3 parity bar (DESIGN.md "GEMM precision").
 //
-// Structure (one persistent CTA per SM, 15 warps):
+// Structure (one persistent CTA per SM, 17 warps):
 //   warps 0-3   epilogue : tcgen05.ld accumulator rows from TMEM -> shared transpose -> (+bias, +C)
 //                          -> 128-byte coalesced global stores
 //   warp  4     MMA      : one lane issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and commits
 //   warps 5-12  A producer: global fp32 A tile -> split -> 128B-swizzled K-major shared tiles, with
 //                          the next k-block's loads in flight during conversion.  (No TMA: the A
 //                          operand needs the fp32 -> 2 x bf16 conversion on the way in.)
-//   warps 13-14 B loader : pre-split bf16 weight tiles -> shared with cp.async (from L2)
+//   warps 13-16 B loader : pre-split weight tiles -> shared with cp.async (from L2), two stages in flight
 // Pipelines: full/empty mbarriers per shared stage, tmem_full/tmem_empty per accumulator buffer
 // (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
 // Every mbarrier wait is bounded; on timeout the kernel raises a status word instead of hanging.
@@ -30,9 +30,9 @@ constexpr int NUM_EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
 constexpr int A_WARP0 = 5;                  // 8 warps convert the fp32 A operand
 constexpr int NUM_A_THREADS = 8 * 32;
-constexpr int B_WARP0 = 13;                 // 2 warps stream the pre-split bf16 B operand (cp.async)
-constexpr int NUM_B_THREADS = 2 * 32;
-constexpr int TC_THREADS = 15 * 32;         // 480
+constexpr int B_WARP0 = 13;                 // 4 warps stream the pre-split B operand (cp.async, 2 stages in flight)
+constexpr int NUM_B_THREADS = 4 * 32;
+constexpr int TC_THREADS = 17 * 32;         // 544
 constexpr int EPI_LD = 36;                  // padded row stride (floats) of the epilogue staging tile
 
 template <int BN, bool TF32>
@@ -202,9 +202,11 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
             t = tn; kb = kbn; have = have_next;
         }
     } else if (warp >= B_WARP0) {
-        // ================================================================ B loaders (pre-split bf16, cp.async)
+        // ================================================================ B loaders (pre-split, cp.async)
+        // Two stages in flight: the copies of k-block i+1 are issued before waiting for those of k-block i
+        // (cp.async groups), so the L2 latency of one stage overlaps the issue of the next.
         const int ptid = tid - B_WARP0 * 32;
-        int stage = 0;
+        int stage = 0, prev_stage = -1;
         uint32_t phase = 0;
         bool ok = true;
         for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
@@ -214,7 +216,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                 const uint32_t sb_hi = smem_u32(smem + stage * cfg::STAGE_BYTES + 2 * cfg::A_BYTES);
                 const uint32_t sb_lo = sb_hi + cfg::B_BYTES;
                 const int k0 = kb * BK;
-#pragma unroll 8
+#pragma unroll 4
                 for (int task = ptid; task < BN * 8; task += NUM_B_THREADS) {
                     const int row = task >> 3, ch = task & 7;
                     const size_t e = ((size_t)(n0 + row) * Kp + k0 + ch * CHUNK) * ESZ;      // byte offset
@@ -222,11 +224,20 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_hi + off), "l"(Bhi + e) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_lo + off), "l"(Blo + e) : "memory");
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                fence_proxy_async();
-                mbar_arrive(full_bar(stage));
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (prev_stage >= 0) {
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");      // the previous stage has landed
+                    fence_proxy_async();
+                    mbar_arrive(full_bar(prev_stage));
+                }
+                prev_stage = stage;
                 if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+        }
+        if (prev_stage >= 0) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            fence_proxy_async();
+            if (ok) mbar_arrive(full_bar(prev_stage));
         }
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer

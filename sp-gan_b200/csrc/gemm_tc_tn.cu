@@ -21,8 +21,8 @@ constexpr int KC = 1024;                     // rows per work unit
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
 constexpr int P_WARP0 = 5;
-constexpr int NUM_P_THREADS = 8 * 32;
-constexpr int TN_THREADS = 13 * 32;          // 416
+constexpr int NUM_P_THREADS = 16 * 32;       // 16 producer warps: scalar transposing loads need the parallelism
+constexpr int TN_THREADS = 21 * 32;          // 672
 constexpr int EPI_LD = 36;
 
 template <int BN>
@@ -59,8 +59,8 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
                   int64_t ldb, float* __restrict__ C, int64_t ldc, int m_tiles, int n_tiles, int64_t k_chunks,
                   int* status, bool vecC) {
     using cfg = CfgTN<BN>;
-    constexpr int A_TASKS = BM * (BK / 4) / NUM_P_THREADS;     // 4 (row, 4-k chunk) tasks per thread
-    constexpr int B_TASKS = BN * (BK / 4) / NUM_P_THREADS;     // 2 / 4 / 8
+    constexpr int A_TASKS = BM * (BK / 4) / NUM_P_THREADS;     // 2 (row, 4-k chunk) tasks per thread
+    constexpr int B_TASKS = BN * (BK / 4) / NUM_P_THREADS;     // 1 / 2 / 4
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
