@@ -147,14 +147,15 @@ int spgan_norm_apply(const float *x, int64_t R, int C, int64_t seg_rows, const f
  * rv = (1-m) rv + m var * R/(R-1); *count += 1 (int64). */
 int spgan_bn_update_running(const float *mean, const float *var, int C, int64_t R, float momentum, float *rm,
                             float *rv, int64_t *count, spgan_stream_t stream);
-/* First-order backward of y = act(norm(x)*gamma+beta): given g = dL/dy (post-activation) it
- * computes sums sg[s,c] = sum g', sgx[s,c] = sum g' * xhat (g' = g masked by the activation
- * via the saved output y), then dx.  dgamma = sum_s sgx, dbeta = sum_s sg. */
-int spgan_norm_bwd_reduce(const float *g, const float *x, const float *y_act, float slope, int64_t R, int C,
-                          int64_t seg_rows, const float *mean, const float *rstd, float *sg, float *sgx,
-                          void *workspace, spgan_stream_t stream);
-int spgan_norm_bwd_apply(const float *g, const float *x, const float *y_act, float slope, int64_t R, int C,
-                         int64_t seg_rows, const float *mean, const float *rstd, const float *gamma,
+/* First-order backward of y = act(norm(x)*gamma+beta): given g = dL/dy (post-activation) it computes
+ * sums sg[s,c] = sum g', sgx[s,c] = sum g' * xhat, where g' = g masked by the LeakyReLU(slope) of the
+ * forward (slope 1 = no activation; the mask is recomputed from x, mean, rstd, gamma, beta with the
+ * forward's arithmetic, nothing else is re-read), then dx.  dgamma = sum_s sgx, dbeta = sum_s sg. */
+int spgan_norm_bwd_reduce(const float *g, const float *x, float slope, int64_t R, int C, int64_t seg_rows,
+                          const float *mean, const float *rstd, const float *gamma, const float *beta, float *sg,
+                          float *sgx, void *workspace, spgan_stream_t stream);
+int spgan_norm_bwd_apply(const float *g, const float *x, float slope, int64_t R, int C, int64_t seg_rows,
+                         const float *mean, const float *rstd, const float *gamma, const float *beta,
                          const float *sg, const float *sgx, float *dx, spgan_stream_t stream);
 /* Second-order (double) backward of train-mode batch norm, needed by the gradient penalty
  * (gradient_penalty.py:31-33 with create_graph=True).  Inputs: first-backward operands

@@ -152,13 +152,19 @@ struct StatsFin {
         if (var) var[o] = (float)v;
     }
 };
+// The LeakyReLU mask of the fused BN+activation is recomputed from x (same fma as the forward) instead of
+// re-reading the activated output: one fewer full-tensor read per pass.
 struct NormBwdOp {
-    const float* g; const float* x; const float* y; float slope; int C; const float* mean; const float* rstd;
+    const float* g; const float* x; float slope; int C; const float* mean; const float* rstd;
+    const float* gamma; const float* beta;
     __device__ void operator()(int64_t r, int c, int64_t seg, float* acc) const {
         const int64_t i = r * C + c;
         float gi = __ldg(g + i);
-        if (y != nullptr && !(__ldg(y + i) > 0.f)) gi *= slope;
         const float xh = (__ldg(x + i) - __ldg(mean + seg * C + c)) * __ldg(rstd + seg * C + c);
+        if (slope != 1.f) {
+            const float pre = fmaf(xh, gamma ? __ldg(gamma + c) : 1.f, beta ? __ldg(beta + c) : 0.f);
+            if (!(pre > 0.f)) gi *= slope;
+        }
         acc[0] += gi; acc[1] = fmaf(gi, xh, acc[1]);
     }
 };
@@ -213,14 +219,18 @@ struct StatsOp4 {
     }
 };
 struct NormBwdOp4 {
-    const float* g; const float* x; const float* y; float slope; int C; const float* mean; const float* rstd;
-    struct State { float4 mean, rstd; };
-    __device__ State init(int c4, int64_t seg) const { return State{ld4(mean + seg * C + c4 * 4), ld4(rstd + seg * C + c4 * 4)}; }
+    const float* g; const float* x; float slope; int C; const float* mean; const float* rstd;
+    const float* gamma; const float* beta;
+    struct State { float4 mean, rstd, gamma, beta; };
+    __device__ State init(int c4, int64_t seg) const {
+        return State{ld4(mean + seg * C + c4 * 4), ld4(rstd + seg * C + c4 * 4),
+                     gamma ? ld4(gamma + c4 * 4) : f4(1.f), beta ? ld4(beta + c4 * 4) : f4(0.f)};
+    }
     __device__ void accum(const State& st, int64_t r, int c4, float4* acc) const {
         const int64_t i = r * C + c4 * 4;
         float4 gi = ld4(g + i);
-        if (y != nullptr) gi = mask4(gi, ld4(y + i), slope);
         const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
+        if (slope != 1.f) gi = mask4(gi, fma4(xh, st.gamma, st.beta), slope);
         acc[0] = add4(acc[0], gi); acc[1] = fma4(gi, xh, acc[1]);
     }
 };
@@ -251,19 +261,20 @@ struct NormApplyOp4 {
     }
 };
 struct NormBwdApplyOp4 {
-    const float* g; const float* x; const float* yact; float slope; int C; float inv_n; const float* mean;
-    const float* rstd; const float* gamma; const float* sg; const float* sgx; float* dx;
-    struct State { float4 mean, rstd, coef, a, b; };     // dx = coef * (g' - a - xh * b)
+    const float* g; const float* x; float slope; int C; float inv_n; const float* mean;
+    const float* rstd; const float* gamma; const float* beta; const float* sg; const float* sgx; float* dx;
+    struct State { float4 mean, rstd, gamma, beta, coef, a, b; };     // dx = coef * (g' - a - xh * b)
     __device__ State init(int c4, int64_t seg) const {
         const float4 m = ld4(mean + seg * C + c4 * 4), r = ld4(rstd + seg * C + c4 * 4);
-        const float4 gm = gamma ? ld4(gamma + c4 * 4) : f4(1.f);
-        return State{m, r, mul4(gm, r), mul4(ld4(sg + seg * C + c4 * 4), f4(inv_n)), mul4(ld4(sgx + seg * C + c4 * 4), f4(inv_n))};
+        const float4 gm = gamma ? ld4(gamma + c4 * 4) : f4(1.f), bt = beta ? ld4(beta + c4 * 4) : f4(0.f);
+        return State{m, r, gm, bt, mul4(gm, r), mul4(ld4(sg + seg * C + c4 * 4), f4(inv_n)),
+                     mul4(ld4(sgx + seg * C + c4 * 4), f4(inv_n))};
     }
     __device__ void apply(const State& st, int64_t r, int c4) const {
         const int64_t i = r * C + c4 * 4;
         float4 gi = ld4(g + i);
-        if (yact != nullptr) gi = mask4(gi, ld4(yact + i), slope);
         const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
+        if (slope != 1.f) gi = mask4(gi, fma4(xh, st.gamma, st.beta), slope);
         st4(dx + i, mul4(st.coef, sub4(sub4(gi, st.a), mul4(xh, st.b))));
     }
 };
@@ -332,19 +343,17 @@ __global__ void norm_apply_kernel(const float* __restrict__ x, int64_t R, int C,
         const int c = (int)(i - r * C);
         const int64_t sc = (r / seg_rows) * C + c;
         float v = (__ldg(x + i) - __ldg(mean + sc)) * __ldg(rstd + sc);
-        if (gamma) v *= __ldg(gamma + c);
-        if (beta) v += __ldg(beta + c);
+        v = fmaf(v, gamma ? __ldg(gamma + c) : 1.f, beta ? __ldg(beta + c) : 0.f);
         y[i] = slope == 1.f ? v : lrelu_f(v, slope);
     }
 }
 
 // dx = gamma * rstd * (g' - sg/n - xhat * sgx/n)
-__global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x,
-                                      const float* __restrict__ yact, float slope, int64_t R, int C,
-                                      int64_t seg_rows, const float* __restrict__ mean,
+__global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x, float slope,
+                                      int64_t R, int C, int64_t seg_rows, const float* __restrict__ mean,
                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                      const float* __restrict__ sg, const float* __restrict__ sgx,
-                                      float* __restrict__ dx) {
+                                      const float* __restrict__ beta, const float* __restrict__ sg,
+                                      const float* __restrict__ sgx, float* __restrict__ dx) {
     const int64_t total = R * C;
     const float inv_n = 1.f / (float)seg_rows;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -352,10 +361,10 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ g, const float* 
         const int c = (int)(i - r * C);
         const int64_t sc = (r / seg_rows) * C + c;
         float gi = __ldg(g + i);
-        if (yact != nullptr && !(__ldg(yact + i) > 0.f)) gi *= slope;
         const float rs = __ldg(rstd + sc);
         const float xh = (__ldg(x + i) - __ldg(mean + sc)) * rs;
         const float gm = gamma ? __ldg(gamma + c) : 1.f;
+        if (slope != 1.f && !(fmaf(xh, gm, beta ? __ldg(beta + c) : 0.f) > 0.f)) gi *= slope;
         dx[i] = gm * rs * (gi - __ldg(sg + sc) * inv_n - xh * __ldg(sgx + sc) * inv_n);
     }
 }
@@ -730,25 +739,24 @@ extern "C" int spgan_bn_update_running(const float* mean, const float* var, int 
     bn_update_running_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(mean, var, C, unbias, momentum, rm, rv, count);
     return spgan_launch_status();
 }
-extern "C" int spgan_norm_bwd_reduce(const float* g, const float* x, const float* y_act, float slope, int64_t R,
-                                     int C, int64_t seg_rows, const float* mean, const float* rstd, float* sg,
-                                     float* sgx, void* ws, spgan_stream_t s) {
+extern "C" int spgan_norm_bwd_reduce(const float* g, const float* x, float slope, int64_t R, int C,
+                                     int64_t seg_rows, const float* mean, const float* rstd, const float* gamma,
+                                     const float* beta, float* sg, float* sgx, void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && R >= 1 && C >= 1);
-    const bool vec = al16(g) && al16(x) && al16(mean) && al16(rstd) && (!y_act || al16(y_act));
-    return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), NormBwdOp{g, x, y_act, slope, C, mean, rstd},
-                            NormBwdOp4{g, x, y_act, slope, C, mean, rstd}, vec, Store2Fin{sg, sgx, C});
+    const bool vec = al16(g) && al16(x) && al16(mean) && al16(rstd) && (!gamma || al16(gamma)) && (!beta || al16(beta));
+    return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), NormBwdOp{g, x, slope, C, mean, rstd, gamma, beta},
+                            NormBwdOp4{g, x, slope, C, mean, rstd, gamma, beta}, vec, Store2Fin{sg, sgx, C});
 }
-extern "C" int spgan_norm_bwd_apply(const float* g, const float* x, const float* y_act, float slope, int64_t R,
-                                    int C, int64_t seg_rows, const float* mean, const float* rstd,
-                                    const float* gamma, const float* sg, const float* sgx, float* dx,
-                                    spgan_stream_t s) {
+extern "C" int spgan_norm_bwd_apply(const float* g, const float* x, float slope, int64_t R, int C, int64_t seg_rows,
+                                    const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                    const float* sg, const float* sgx, float* dx, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && dx && R >= 1 && C >= 1 && seg_rows >= 1);
     if (C % 4 == 0 && R % seg_rows == 0 && al16(g) && al16(x) && al16(dx) && al16(mean) && al16(rstd) && al16(sg) &&
-        al16(sgx) && (!gamma || al16(gamma)) && (!y_act || al16(y_act)))
+        al16(sgx) && (!gamma || al16(gamma)) && (!beta || al16(beta)))
         return fastnorm::run_map(R, C, seg_rows, as_stream(s),
-                                 NormBwdApplyOp4{g, x, y_act, slope, C, 1.f / (float)seg_rows, mean, rstd, gamma, sg, sgx, dx});
-    norm_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, x, y_act, slope, R, C, seg_rows, mean,
-                                                                             rstd, gamma, sg, sgx, dx);
+                                 NormBwdApplyOp4{g, x, slope, C, 1.f / (float)seg_rows, mean, rstd, gamma, beta, sg, sgx, dx});
+    norm_bwd_apply_kernel<<<ew_grid(R * C, 256, 16), 256, 0, as_stream(s)>>>(g, x, slope, R, C, seg_rows, mean, rstd,
+                                                                             gamma, beta, sg, sgx, dx);
     return spgan_launch_status();
 }
 extern "C" int spgan_bn_dbl_bwd_reduce(const float* g, const float* u, const float* x, int64_t R, int C,

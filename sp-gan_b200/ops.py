@@ -464,18 +464,20 @@ def col_stats(x, seg_rows, eps):
     return mean, rstd, var
 
 
-def _norm_bwd(g, x, y_act, slope, seg_rows, mean, rstd, gamma):
+def _norm_bwd(g, x, slope, seg_rows, mean, rstd, gamma, beta):
+    """(dx, sum g', sum g' xhat) of y = LeakyReLU_slope(norm(x) * gamma + beta); the activation mask is
+    recomputed from x inside the kernels (slope 1 = no activation)."""
     R, C = x.shape
     nseg = R // seg_rows
     sg = torch.empty((nseg, C), device=x.device, dtype=torch.float32)
     sgx = torch.empty_like(sg)
-    yp = y_act.data_ptr() if y_act is not None else None
-    L().norm_bwd_reduce(g.data_ptr(), x.data_ptr(), yp, slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(),
+    gp = gamma.data_ptr() if gamma is not None else None
+    bp = beta.data_ptr() if beta is not None else None
+    L().norm_bwd_reduce(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
                         sg.data_ptr(), sgx.data_ptr(), _ws(R, C, seg_rows, 2, x.device).data_ptr(), _stream())
     dx = torch.empty_like(x)
-    L().norm_bwd_apply(g.data_ptr(), x.data_ptr(), yp, slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(),
-                       gamma.data_ptr() if gamma is not None else None, sg.data_ptr(), sgx.data_ptr(),
-                       dx.data_ptr(), _stream())
+    L().norm_bwd_apply(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
+                       sg.data_ptr(), sgx.data_ptr(), dx.data_ptr(), _stream())
     return dx, sg, sgx
 
 
@@ -512,7 +514,7 @@ class BatchNormTrainBwd(Function):
     def forward(ctx, g, x, gamma, mean, rstd):
         g = _c(g)
         ctx.set_materialize_grads(False)
-        dx, sg, sgx = _norm_bwd(g, x, None, 1.0, x.shape[0], mean, rstd, gamma)
+        dx, sg, sgx = _norm_bwd(g, x, 1.0, x.shape[0], mean, rstd, gamma, None)
         ctx.save_for_backward(g, x, gamma, mean, rstd)
         return dx, sgx.view(-1), sg.view(-1)
 
@@ -551,16 +553,16 @@ class BatchNormActTrain(Function):
         L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                        slope, y.data_ptr(), _stream())
         ctx.slope = slope
-        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.mark_non_differentiable(mean, var)
         return y, mean, var
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy, _gm, _gv):
-        x, y, gamma, mean, rstd = ctx.saved_tensors
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
         gy = _c(gy)
-        dx, sg, sgx = _norm_bwd(gy, x, y, ctx.slope, x.shape[0], mean, rstd, gamma)
+        dx, sg, sgx = _norm_bwd(gy, x, ctx.slope, x.shape[0], mean, rstd, gamma, beta)
         return dx, sgx.view(-1), sg.view(-1), None, None
 
 
@@ -575,21 +577,21 @@ class NormAffineEval(Function):
         L().norm_apply(x.data_ptr(), R, C, R, rm.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                        slope, y.data_ptr(), _stream())
         ctx.slope = slope
-        ctx.save_for_backward(x, y, gamma, rm, rstd)
+        ctx.save_for_backward(x, y, gamma, beta, rm, rstd)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, y, gamma, rm, rstd = ctx.saved_tensors
+        x, y, gamma, beta, rm, rstd = ctx.saved_tensors
         gy = _c(gy)
         R, C = x.shape
         # frozen statistics: dx = g' * gamma * rstd, dgamma = sum g' xhat, dbeta = sum g'
         sg = torch.empty((1, C), device=x.device, dtype=torch.float32)
         sgx = torch.empty_like(sg)
-        yp = y.data_ptr() if ctx.slope != 1.0 else None
-        L().norm_bwd_reduce(gy.data_ptr(), x.data_ptr(), yp, ctx.slope, R, C, R, rm.data_ptr(), rstd.data_ptr(),
-                            sg.data_ptr(), sgx.data_ptr(), _ws(R, C, R, 2, x.device).data_ptr(), _stream())
+        L().norm_bwd_reduce(gy.data_ptr(), x.data_ptr(), ctx.slope, R, C, R, rm.data_ptr(), rstd.data_ptr(),
+                            gamma.data_ptr(), beta.data_ptr(), sg.data_ptr(), sgx.data_ptr(),
+                            _ws(R, C, R, 2, x.device).data_ptr(), _stream())
         gmask = gy
         if ctx.slope != 1.0:
             gmask = torch.empty_like(gy)
@@ -629,7 +631,7 @@ class AdaIN(Function):
                       ds.data_ptr() if ds is not None else None, gxh.data_ptr() if gxh is not None else None, _stream())
         dx = None
         if gxh is not None:
-            dx, _, _ = _norm_bwd(gxh, x, None, 1.0, ctx.seg_rows, mean, rstd, None)
+            dx, _, _ = _norm_bwd(gxh, x, 1.0, ctx.seg_rows, mean, rstd, None, None)
         return dx, ds, None, None
 
 
