@@ -270,6 +270,185 @@ knn_group_kernel(const float* __restrict__ x, const float* __restrict__ xs, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast variant for N % 4 == 0 and C <= 128 (every shape on the generator's path): the 64-query tile
+// stays resident in shared memory for the whole kernel, candidate chunks are double buffered with
+// cp.async (loads of chunk i+1 overlap the FMA chains of chunk i), and the selection phase rejects a
+// whole 4-candidate group per lane with one ballot in the common case.  Arithmetic and tie order are
+// identical to knn_group_kernel (same FMA chains, same (dist, index) lists).
+// ---------------------------------------------------------------------------------------
+constexpr int QMAXC = 128;
+
+struct KnnFastSmem {
+    float q[QMAXC][QT];          // 32 KB, channel-major, resident
+    float c[2][CK][CT];          // 32 KB, double buffered candidate chunk
+    float d[QT][CT + DPAD];      // 33 KB
+    float xs_q[QT];
+    float xs_c[2][CT];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;            // src-size 0 => zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_group_fast_kernel(const float* __restrict__ x, const float* __restrict__ xs, int B, int C, int N, int k,
+                      int32_t* __restrict__ idx, float* __restrict__ ee) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KnnFastSmem& s = *reinterpret_cast<KnnFastSmem*>(smem_raw);
+    __shared__ int nbr[QT][32];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int q_tiles = (N + QT - 1) / QT;
+    const int b = blockIdx.x / q_tiles;
+    const int i0 = (blockIdx.x % q_tiles) * QT;
+    const float* xb = x + (int64_t)b * C * N;
+    const float* xsb = xs + (int64_t)b * N;
+    const int K1 = k + 1;
+    const int n_chunks = (C + CK - 1) / CK;
+    const int n_tiles = (N + CT - 1) / CT;
+    const int total = n_tiles * n_chunks;
+
+    // resident query tile (zero beyond N / C)
+    for (int e = tid; e < C * (QT / 4); e += KNN_THREADS) {
+        const int ch = e / (QT / 4), q4 = (e % (QT / 4)) * 4;
+        cp_async16(&s.q[ch][q4], xb + (int64_t)ch * N + i0 + q4, i0 + q4 < N);
+    }
+    if (tid < QT) s.xs_q[tid] = (i0 + tid < N) ? xsb[i0 + tid] : 0.f;
+    auto stage = [&](int it, int buf) {          // it -> (tile, chunk)
+        const int tile = it / n_chunks, chunk = it % n_chunks;
+        const int j0 = tile * CT, c0 = chunk * CK;
+        for (int e = tid; e < CK * (CT / 4); e += KNN_THREADS) {
+            const int cc = e / (CT / 4), j4 = (e % (CT / 4)) * 4;
+            const int ch = c0 + cc;
+            cp_async16(&s.c[buf][cc][j4], xb + (int64_t)(ch < C ? ch : 0) * N + j0 + j4, ch < C && j0 + j4 < N);
+        }
+        if (chunk == 0 && tid < CT) s.xs_c[tile & 1][tid] = (j0 + tid < N) ? xsb[j0 + tid] : 0.f;
+    };
+    stage(0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    float ld[8];
+    int lj[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { ld[u] = FLT_MAX; lj[u] = 0x7fffffff; }
+
+    float acc[4][8];
+    for (int it = 0; it < total; ++it) {
+        const int tile = it / n_chunks, chunk = it % n_chunks;
+        const int buf = it & 1;
+        if (chunk == 0) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                          // chunk `it` visible; everyone is done with buffer buf^1
+        if (it + 1 < total) stage(it + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+
+        const int c0 = chunk * CK;
+        const int cmax = min(CK, C - c0);
+#pragma unroll 4
+        for (int cc = 0; cc < cmax; ++cc) {
+            const float4 qv = *reinterpret_cast<const float4*>(&s.q[c0 + cc][ty * 4]);
+            const float4 c0v = *reinterpret_cast<const float4*>(&s.c[buf][cc][tx * 4]);
+            const float4 c1v = *reinterpret_cast<const float4*>(&s.c[buf][cc][64 + tx * 4]);
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+            const float ca[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[a][c] = __fmaf_rn(qa[a], ca[c], acc[a][c]);
+        }
+        if (chunk != n_chunks - 1) continue;
+
+        // ---- tile complete: distances -> shared, then selection
+        const int j0 = tile * CT;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const float xq = s.xs_q[ty * 4 + a];
+            float out[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int jj = (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
+                out[c] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[tile & 1][jj]);
+            }
+            *reinterpret_cast<float4*>(&s.d[ty * 4 + a][tx * 4]) = make_float4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<float4*>(&s.d[ty * 4 + a][64 + tx * 4]) = make_float4(out[4], out[5], out[6], out[7]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int qq = warp * 8 + u;
+            const float4 dv = *reinterpret_cast<const float4*>(&s.d[qq][lane * 4]);
+            const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+            float tau = __shfl_sync(0xffffffffu, ld[u], K1 - 1);
+            int tauj = __shfl_sync(0xffffffffu, lj[u], K1 - 1);
+            const int jb = j0 + lane * 4;
+            // common case: none of the lane's 4 candidates beats the current k-th best
+            bool any = false;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) any |= (jb + t < N) && lex_less(dd[t], jb + t, tau, tauj);
+            if (__ballot_sync(0xffffffffu, any) == 0u) continue;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int j = jb + t;
+                const float d = dd[t];
+                bool pass = (j < N) && lex_less(d, j, tau, tauj);
+                unsigned m = __ballot_sync(0xffffffffu, pass);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    const float nd = __shfl_sync(0xffffffffu, d, src);
+                    const int nj = __shfl_sync(0xffffffffu, j, src);
+                    const bool before = (lane < K1) && lex_less(ld[u], lj[u], nd, nj);
+                    const int pos = __popc(__ballot_sync(0xffffffffu, before));
+                    const float upd = __shfl_up_sync(0xffffffffu, ld[u], 1);
+                    const int upj = __shfl_up_sync(0xffffffffu, lj[u], 1);
+                    if (lane == pos) { ld[u] = nd; lj[u] = nj; }
+                    else if (lane > pos && lane < K1) { ld[u] = upd; lj[u] = upj; }
+                    tau = __shfl_sync(0xffffffffu, ld[u], K1 - 1);
+                    tauj = __shfl_sync(0xffffffffu, lj[u], K1 - 1);
+                    pass = pass && (lane != src) && lex_less(d, j, tau, tauj);
+                    m = __ballot_sync(0xffffffffu, pass);
+                }
+            }
+        }
+        // the next iteration's top-of-loop barrier orders these reads of s.d before the next tile's writes
+    }
+
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int qq = warp * 8 + u;
+        const int i = i0 + qq;
+        if (lane >= 1 && lane < K1) {
+            nbr[qq][lane - 1] = lj[u];
+            if (i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = lj[u];
+        }
+    }
+    if (ee == nullptr) return;
+    __syncthreads();
+    const int nq = min(QT, N - i0);
+    const int per_ch = nq * k;
+    for (int c = 0; c < C; ++c) {
+        const float* row = xb + (int64_t)c * N;
+        float* e_ctr = ee + (((int64_t)b * 2 * C + c) * N + i0) * k;
+        float* e_dif = ee + (((int64_t)b * 2 * C + C + c) * N + i0) * k;
+        for (int e = tid; e < per_ch; e += KNN_THREADS) {
+            const int qq = e / k, r = e - qq * k;
+            const float ctr = __ldg(row + i0 + qq);
+            const float nb = __ldg(row + nbr[qq][r]);
+            e_ctr[e] = ctr;
+            e_dif[e] = nb - ctr;
+        }
+    }
+}
+
 __global__ void group_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int B, int C, int N,
                              int k, float* __restrict__ ee) {
     // grid: (ceil(N*k / 256), C, B)
@@ -318,6 +497,15 @@ extern "C" int spgan_knn_group(const float* x, const float* xs, int B, int C, in
     const int q_tiles = (N + QT - 1) / QT;
     const int64_t grid = (int64_t)B * q_tiles;
     if (grid > 0x7fffffffLL) return SPGAN_E_UNSUPPORTED;
+    if (N % 4 == 0 && C <= QMAXC && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        static_assert(sizeof(KnnFastSmem) <= 104 * 1024, "two CTAs per SM");
+        e = cudaFuncSetAttribute(knn_group_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(KnnFastSmem));
+        if (e != cudaSuccess) return (int)e;
+        knn_group_fast_kernel<<<(unsigned)grid, KNN_THREADS, sizeof(KnnFastSmem), as_stream(stream)>>>(x, xs, B, C, N, k,
+                                                                                                     idx, ee);
+        return spgan_launch_status();
+    }
     knn_group_kernel<<<(unsigned)grid, KNN_THREADS, sizeof(KnnSmem), as_stream(stream)>>>(x, xs, B, C, N, k, idx, ee);
     return spgan_launch_status();
 }
