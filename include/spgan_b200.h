@@ -94,7 +94,8 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  *             weight-gradient form transA == 1, transB == 0 with K >= 4096 and M, N >= 16 (accumulated
  *             in TMEM per 1024 rows of K and flushed into C with fp32 atomics);
  *             both need a workspace of spgan_gemm_workspace(engine, N, K) bytes (256-byte aligned).
- *             Anything else runs on engine 0.
+ *             Anything else runs on engine 0, which uses the workspace (if given) for deterministic
+ *             split-K partial tiles when M <= 128 and 256 <= K < 2048 (the small-batch MLPs).
  * The first int of the workspace is a status word: non-zero after completion means the kernel
  * aborted on an internal pipeline timeout (never expected; checked by the tests). */
 size_t spgan_gemm_workspace(int engine, int N, int K);

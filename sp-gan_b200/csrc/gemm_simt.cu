@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_simt_kernel(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda,
                  const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
                  const float* __restrict__ bias, int accumulate, int64_t k_per_split, bool vecA, bool vecB,
-                 bool vecC, bool atomic_out) {
+                 bool vecC, bool atomic_out, int64_t c_split_stride) {
     constexpr int TN = BN / 16;           // columns per thread (8 or 4)
     __shared__ __align__(16) float As[2][BK][BM + APAD];
     __shared__ __align__(16) float Bs[2][BK][BN + APAD];
@@ -146,6 +146,7 @@ gemm_simt_kernel(int64_t M, int N, int64_t K, const float* __restrict__ A, int64
     }
 
     // ---- epilogue
+    C += (int64_t)blockIdx.z * c_split_stride;          // deterministic split-K: every split owns a partial tile
     const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -182,11 +183,57 @@ gemm_simt_kernel(int64_t M, int N, int64_t K, const float* __restrict__ A, int64
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// out[m,n] = sum_z partial[z][m][n] (+ bias[n]) (+ out[m,n]): fixed summation order => deterministic
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t M, int N,
+                                     float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
+                                     int accumulate) {
+    const int64_t total = M * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / N;
+        const int n = (int)(i - m * N);
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += __ldg(partial + (int64_t)z * total + i);
+        if (bias) s += __ldg(bias + n);
+        float* cp = C + m * ldc + n;
+        *cp = accumulate ? *cp + s : s;
+    }
+}
+
+constexpr int kSmallMSplits = 16;
+constexpr int kSmallMRows = 128;
+
 template <int BN>
 int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float* A, int64_t lda, const float* B,
-                int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st) {
+                int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st,
+                void* workspace, size_t workspace_bytes) {
     const int64_t mt = ceil_div64(M, BM);
     const int nt = (N + BN - 1) / BN;
+    // small-batch shapes (the critic's MLP on B rows, the generator's global MLP): a handful of CTAs would walk
+    // K serially.  Split K over up to 16 CTAs per tile into private partial tiles, then reduce in a fixed order.
+    if (mt == 1 && M <= kSmallMRows && K >= 256 && K < 2048 && workspace != nullptr) {
+        int splits = (int)(K / 64);
+        if (splits > kSmallMSplits) splits = kSmallMSplits;
+        const size_t need = (size_t)splits * M * N * sizeof(float);
+        if (splits > 1 && workspace_bytes >= need) {
+            float* partial = reinterpret_cast<float*>(workspace);
+            const int64_t kps = ceil_div64(ceil_div64(K, splits), BK) * BK;
+            splits = (int)ceil_div64(K, kps);
+            const bool vecA = (lda % 4 == 0) && aligned16(A);
+            const bool vecB = (ldb % 4 == 0) && aligned16(B);
+            const bool vecP = (N % 4 == 0) && aligned16(partial);
+            dim3 grid(1, (unsigned)nt, (unsigned)splits);
+#define SPGAN_LAUNCH_P(TA, TB)                                                                                 \
+    gemm_simt_kernel<BN, TA, TB><<<grid, GEMM_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, partial, N, nullptr, 0, kps, \
+                                                                 vecA, vecB, vecP, false, M * (int64_t)N)
+            if (!transA && !transB) SPGAN_LAUNCH_P(false, false);
+            else if (!transA && transB) SPGAN_LAUNCH_P(false, true);
+            else if (transA && !transB) SPGAN_LAUNCH_P(true, false);
+            else SPGAN_LAUNCH_P(true, true);
+#undef SPGAN_LAUNCH_P
+            splitk_reduce_kernel<<<ew_grid(M * N, 256), 256, 0, st>>>(partial, splits, M, N, C, ldc, bias, accumulate);
+            return spgan_launch_status();
+        }
+    }
     // split-K (fp32 atomics) when the output grid cannot fill the machine and K is long: weight gradients,
     // K = #points.  Forward-path shapes (K <= 1280) never split, so forward results are run-to-run
     // deterministic.
@@ -214,7 +261,7 @@ int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float
     dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)splits);
 #define SPGAN_LAUNCH(TA, TB)                                                                              \
     gemm_simt_kernel<BN, TA, TB><<<grid, GEMM_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, \
-                                                                 accumulate, kps, vecA, vecB, vecC, atomic_out)
+                                                                 accumulate, kps, vecA, vecB, vecC, atomic_out, 0)
     if (!transA && !transB) SPGAN_LAUNCH(false, false);
     else if (!transA && transB) SPGAN_LAUNCH(false, true);
     else if (transA && !transB) SPGAN_LAUNCH(true, false);
@@ -226,9 +273,13 @@ int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float
 }  // namespace
 
 int spgan_gemm_simt(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
-                    int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st) {
-    if (N <= 64) return launch_simt<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st);
-    return launch_simt<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st);
+                    int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st,
+                    void* workspace, size_t workspace_bytes) {
+    if (N <= 64)
+        return launch_simt<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st, workspace,
+                               workspace_bytes);
+    return launch_simt<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st, workspace,
+                            workspace_bytes);
 }
 
 
@@ -244,8 +295,11 @@ int spgan_gemm_tc_tn(int64_t Mo, int No, int64_t K, const float* A, int64_t lda,
                      int64_t ldc, int accumulate, void* workspace, cudaStream_t st);
 
 extern "C" size_t spgan_gemm_workspace(int engine, int N, int K) {
-    if ((engine != 1 && engine != 2) || N < 1 || K < 1) return 0;
-    return spgan_gemm_tc_workspace(N, K);
+    if (N < 1 || K < 1) return 0;
+    // deterministic split-K partial tiles of the small-batch path (any engine)
+    const size_t small_m = (K >= 256 && K < 2048) ? (size_t)kSmallMSplits * kSmallMRows * N * sizeof(float) : 0;
+    const size_t tc = (engine == 1 || engine == 2) ? spgan_gemm_tc_workspace(N, K) : 0;
+    return small_m > tc ? small_m : tc;
 }
 
 extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda,
@@ -263,5 +317,6 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
         bias == nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
         spgan_gemm_tc_tn_supported(M, N, K, A, lda, B, ldb))
         return spgan_gemm_tc_tn(M, N, K, A, lda, B, ldb, C, ldc, accumulate, workspace, as_stream(stream));
-    return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream));
+    return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream),
+                           workspace, workspace_bytes);
 }

@@ -153,11 +153,13 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
         bias = _c(bias)
     engine = GEMM_ENGINE if engine is None else engine
     ws, ws_bytes = None, 0
-    if engine in (1, 2) and ((not ta and M >= 128 and N >= 16 and K >= 16) or
-                             (ta and not tb and bias is None and K >= 4096 and M >= 16 and N >= 16)):
+    tc = engine in (1, 2) and ((not ta and M >= 128 and N >= 16 and K >= 16) or
+                               (ta and not tb and bias is None and K >= 4096 and M >= 16 and N >= 16))
+    if tc or (M <= 128 and 256 <= K < 2048):         # tensor-core operands / small-batch split-K partial tiles
         ws_bytes = L().gemm_workspace(engine, N, K)
         ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
-        LAST_TC_WORKSPACE = ws
+        if tc:
+            LAST_TC_WORKSPACE = ws
     L().gemm(int(ta), int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
              bias.data_ptr() if bias is not None else None, int(accumulate), engine,
              ws.data_ptr() if ws is not None else None, ws_bytes, _stream())

@@ -47,6 +47,21 @@ def test_gemm_all_layouts(ta, tb, M, N, K):
     close(out2, (2 * ref - bias.double()).float(), 1e-5, "gemm accumulate")
 
 
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(64, 512, 1024), (64, 1, 64), (4, 256, 512), (128, 1024, 512), (64, 64, 256)])
+def test_gemm_small_batch_split_k_is_deterministic(M, N, K, ta, tb):
+    """Critic MLP shapes (M = batch rows): split-K through private partial tiles, fixed reduction order."""
+    ops = _ops()
+    A = rnd(K, M, seed=61) if ta else rnd(M, K, seed=61)
+    B = rnd(N, K, seed=62) if tb else rnd(K, N, seed=62)
+    bias = rnd(N, seed=63)
+    ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double() + bias.double()
+    o1 = ops.gemm_raw(A.cuda(), B.cuda(), bias.cuda(), ta, tb)
+    o2 = ops.gemm_raw(A.cuda(), B.cuda(), bias.cuda(), ta, tb)
+    close(o1, ref.float(), 1e-5, "small-batch gemm")
+    assert torch.equal(o1, o2)
+
+
 def test_gemm_strided_operands_and_unaligned_slices():
     ops = _ops()
     X = rnd(500, 64, seed=4).cuda()
