@@ -2,7 +2,8 @@
 //
 // Precision: every fp32 operand is split into two narrow terms x = hi + lo and the product is formed
 // as Ahi*Bhi + Ahi*Blo + Alo*Bhi on the 5th-gen tensor cores with fp32 accumulation in TMEM:
-//   TF32 mode (engine 1, default): hi = rna_tf32(x), lo = rna_tf32(x - hi): 22 significant bits,
+//   TF32 mode (engine 1, default): hi = rna_tf32(x), lo = rna_tf32(x - hi) (integer rounding, 2 full-rate
+//       ops each -- cvt.rna.tf32 is a 16-lane/clk instruction): 22 significant bits,
 //       ~2^-21 relative per product -- indistinguishable from an fp32 FMA chain at K <= 1280;
 //   BF16 mode (engine 2, "fast"): hi = trunc_bf16(x), lo = rn_bf16(x - hi): ~2^-16 per product,
 //       twice the MMA rate; NOT used by default because train-mode BatchNorm and the gradient
@@ -48,8 +49,10 @@ struct Cfg {
     // this cuts that count by 3 (measured: rms error ~7e-9*K -> ~2.4e-9*K).
     static constexpr int NACC = TF32 ? 2 : 1;
     static constexpr int TMEM_COLS = 2 * NACC * BN;      // two tile buffers; power of two <= 512
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * 36 * 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                      NUM_EPI_WARPS * 32 * 36 * 4 /*epilogue staging*/;
+                                      EPI_BYTES /*epilogue staging*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 using namespace tc;
@@ -126,10 +129,14 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t m_tiles = (M + BM - 1) / BM;
-    const int64_t total_tiles = m_tiles * n_tiles;
+    const int m_tiles = (int)((M + BM - 1) / BM);
     const int KB = Kp / BK;
     volatile int* vstatus = status;
+    // persistent tile walk t = blockIdx.x, += gridDim.x over (m_tile, n_tile) pairs, n fastest: kept as two
+    // small integers updated incrementally -- no 64-bit divisions inside the role loops
+    const int g_div = (int)gridDim.x / n_tiles, g_mod = (int)gridDim.x % n_tiles;
+    const int mt0 = (int)blockIdx.x / n_tiles, nt0 = (int)blockIdx.x % n_tiles;
+    auto tile_next = [&](int& mt, int& nt) { nt += g_mod; mt += g_div; if (nt >= n_tiles) { nt -= n_tiles; ++mt; } };
 
     if (warp >= A_WARP0 && warp < B_WARP0) {
         // ================================================================ A producers (fp32 -> bf16 hi/lo)
@@ -140,24 +147,37 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         constexpr int V = TF32 ? 1 : 2;                        // float4 loads per task
         const int ptid = tid - A_WARP0 * 32;
         float4 cur[V * TASKS], nxt[V * TASKS];
-        auto load_a = [&](int64_t t, int kb, float4* r) {
-            const int64_t m0 = (t / n_tiles) * BM;
-            const int k0 = kb * BK;
-            const bool fullk = vecA && (k0 + BK <= K);
+        // loop invariants of this thread's tasks: swizzled shared offset and column offset inside a k-block
+        uint32_t soff[TASKS];
+        int colo[TASKS];
+        const float* rowp[TASKS];                              // row pointers of the tile being LOADED
+#pragma unroll
+        for (int j = 0; j < TASKS; ++j) {
+            const int task = ptid + j * NUM_A_THREADS;
+            soff[j] = swz(task >> 3, task & 7);
+            colo[j] = (task & 7) * CHUNK;
+        }
+        auto set_rows = [&](int mt) {
 #pragma unroll
             for (int j = 0; j < TASKS; ++j) {
-                const int task = ptid + j * NUM_A_THREADS;
-                const int row = task >> 3, ch = task & 7;
-                int64_t gm = m0 + row;
+                int64_t gm = (int64_t)mt * BM + ((ptid + j * NUM_A_THREADS) >> 3);
                 if (gm >= M) gm = M - 1;                       // clamp: rows beyond M are never stored
-                const float* src = A + gm * lda + k0 + ch * CHUNK;
-                if (fullk) {
+                rowp[j] = A + gm * lda + colo[j];
+            }
+        };
+        auto load_a = [&](int kb, float4* r) {
+            const int k0 = kb * BK;
+            if (vecA && (k0 + BK <= K)) {
 #pragma unroll
-                    for (int q = 0; q < V; ++q) r[V * j + q] = __ldg(reinterpret_cast<const float4*>(src) + q);
-                } else {
+                for (int j = 0; j < TASKS; ++j)
+#pragma unroll
+                    for (int q = 0; q < V; ++q) r[V * j + q] = __ldg(reinterpret_cast<const float4*>(rowp[j] + k0) + q);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TASKS; ++j) {
                     float v[CHUNK];
 #pragma unroll
-                    for (int e = 0; e < CHUNK; ++e) v[e] = (k0 + ch * CHUNK + e < K) ? __ldg(src + e) : 0.f;
+                    for (int e = 0; e < CHUNK; ++e) v[e] = (k0 + colo[j] + e < K) ? __ldg(rowp[j] + k0 + e) : 0.f;
 #pragma unroll
                     for (int q = 0; q < V; ++q) r[V * j + q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
@@ -165,23 +185,19 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         };
         int stage = 0;
         uint32_t phase = 0;
-        int64_t t = blockIdx.x;
-        int kb = 0;
-        bool have = t < total_tiles;
-        if (have) load_a(t, kb, cur);
+        // the load cursor (lmt, lnt, lkb) runs one k-block ahead of the convert cursor
+        int lmt = mt0, lnt = nt0, lkb = 0;
+        bool have = lmt < m_tiles;
+        if (have) { set_rows(lmt); load_a(0, cur); }
         while (have) {
-            int64_t tn = t;
-            int kbn = kb + 1;
-            if (kbn == KB) { kbn = 0; tn += gridDim.x; }
-            const bool have_next = tn < total_tiles;
-            if (have_next) load_a(tn, kbn, nxt);
+            if (++lkb == KB) { lkb = 0; tile_next(lmt, lnt); if (lmt < m_tiles) set_rows(lmt); }
+            const bool have_next = lmt < m_tiles;
+            if (have_next) load_a(lkb, nxt);
             if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) break;
             unsigned char* sa_hi = smem + stage * cfg::STAGE_BYTES;
             unsigned char* sa_lo = sa_hi + cfg::A_BYTES;
 #pragma unroll
             for (int j = 0; j < TASKS; ++j) {
-                const int task = ptid + j * NUM_A_THREADS;
-                const int row = task >> 3, ch = task & 7;
                 uint4 hi, lo;
                 if constexpr (TF32) {
                     split4_tf32(cur[j], hi, lo);
@@ -190,16 +206,15 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                                         cur[2 * j + 1].x, cur[2 * j + 1].y, cur[2 * j + 1].z, cur[2 * j + 1].w};
                     split8(v, hi, lo);
                 }
-                const uint32_t off = swz(row, ch);
-                *reinterpret_cast<uint4*>(sa_hi + off) = hi;
-                *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+                *reinterpret_cast<uint4*>(sa_hi + soff[j]) = hi;
+                *reinterpret_cast<uint4*>(sa_lo + soff[j]) = lo;
             }
             fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
             mbar_arrive(full_bar(stage));
             if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
             for (int j = 0; j < V * TASKS; ++j) cur[j] = nxt[j];
-            t = tn; kb = kbn; have = have_next;
+            have = have_next;
         }
     } else if (warp >= B_WARP0) {
         // ================================================================ B loaders (pre-split, cp.async)
@@ -209,17 +224,20 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         int stage = 0, prev_stage = -1;
         uint32_t phase = 0;
         bool ok = true;
-        for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-            const int n0 = (int)(t % n_tiles) * BN;
+        constexpr int BT = BN * 8 / NUM_B_THREADS;            // tasks per thread
+        const uint32_t row_bytes = (uint32_t)Kp * ESZ;
+        for (int mt = mt0, nt = nt0; mt < m_tiles && ok; tile_next(mt, nt)) {
+            const uint32_t tile_off = (uint32_t)(nt * BN) * row_bytes;          // 32-bit: B is at most a few MB
             for (int kb = 0; kb < KB; ++kb) {
                 if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) { ok = false; break; }
                 const uint32_t sb_hi = smem_u32(smem + stage * cfg::STAGE_BYTES + 2 * cfg::A_BYTES);
                 const uint32_t sb_lo = sb_hi + cfg::B_BYTES;
-                const int k0 = kb * BK;
-#pragma unroll 4
-                for (int task = ptid; task < BN * 8; task += NUM_B_THREADS) {
+                const uint32_t k_off = tile_off + (uint32_t)(kb * BK) * ESZ;
+#pragma unroll
+                for (int j = 0; j < BT; ++j) {
+                    const int task = ptid + j * NUM_B_THREADS;
                     const int row = task >> 3, ch = task & 7;
-                    const size_t e = ((size_t)(n0 + row) * Kp + k0 + ch * CHUNK) * ESZ;      // byte offset
+                    const uint32_t e = k_off + (uint32_t)row * row_bytes + (uint32_t)(ch * CHUNK) * ESZ;
                     const uint32_t off = swz(row, ch);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_hi + off), "l"(Bhi + e) : "memory");
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_lo + off), "l"(Blo + e) : "memory");
@@ -242,10 +260,11 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer
         constexpr uint32_t idesc = make_idesc(BM, BN, TF32);
+        constexpr uint32_t idesc2 = make_idesc(BM, (TF32 && BN <= 128) ? 2 * BN : BN, TF32);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         bool ok = true;
-        for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+        for (int mt = mt0, nt = nt0; mt < m_tiles && ok; tile_next(mt, nt)) {
             if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1, vstatus)) { ok = false; break; }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * cfg::NACC * BN);
@@ -264,9 +283,17 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                     for (int kk = 0; kk < 4; ++kk) {                      // 4 MMA k-steps of 32 bytes per row
                         const uint64_t adv = (uint64_t)(kk * 2);          // 32 bytes >> 4
                         const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
-                        umma<TF32>(tmem_d, dah + adv, dbh + adv, idesc, first);
-                        umma<TF32>(tmem_x, dah + adv, dbl + adv, idesc, TF32 ? first : 1u);
-                        umma<TF32>(tmem_x, dal + adv, dbh + adv, idesc, 1u);
+                        if constexpr (TF32) {
+                            // [main | cross] += Ahi x [Bhi ; Blo] as ONE N = 2*BN instruction (the two B halves and
+                            // the two accumulators are adjacent), then cross += Alo x Bhi: the A tile is read from
+                            // shared memory twice instead of three times
+                            umma<true>(tmem_d, dah + adv, dbh + adv, idesc2, first);
+                            umma<true>(tmem_x, dal + adv, dbh + adv, idesc, 1u);
+                        } else {
+                            umma<false>(tmem_d, dah + adv, dbh + adv, idesc, first);
+                            umma<false>(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+                            umma<false>(tmem_d, dal + adv, dbh + adv, idesc, 1u);
+                        }
                     }
                     umma_commit(empty_bar(stage));        // frees the stage once the MMAs have read it
                 }
@@ -287,9 +314,9 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         int acc = 0;
         uint32_t acc_phase = 0;
         bool ok = true;
-        for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-            const int64_t m0 = (t / n_tiles) * BM + warp * 32;
-            const int n0 = (int)(t % n_tiles) * BN;
+        for (int mt = mt0, nt = nt0; mt < m_tiles && ok; tile_next(mt, nt)) {
+            const int64_t m0 = (int64_t)mt * BM + warp * 32;
+            const int n0 = nt * BN;
             if (!mbar_wait(tfull_bar(acc), acc_phase, vstatus)) { ok = false; break; }
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * cfg::NACC * BN);
@@ -370,10 +397,8 @@ __global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int 
         float v = 0.f;
         if (n < N && k < K) v = transB ? __ldg(B + (int64_t)n * ldb + k) : __ldg(B + (int64_t)k * ldb + n);
         if constexpr (TF32) {
-            uint32_t h, l;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-            const float r = v - __uint_as_float(h);
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+            const uint32_t h = tf32_rna_bits(v);
+            const uint32_t l = tf32_rna_bits(v - __uint_as_float(h));
             reinterpret_cast<uint32_t*>(hi_)[i] = h;
             reinterpret_cast<uint32_t*>(lo_)[i] = l;
         } else {

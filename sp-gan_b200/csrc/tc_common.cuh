@@ -84,15 +84,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 
+// fp32 -> tf32 with round-to-nearest (ties away from zero, like cvt.rna.tf32.f32) in two full-rate integer
+// ops.  cvt.rna runs on the 16-lane/clk conversion unit and made the A-operand producers the bottleneck
+// of the TF32x3 GEMM (2 conversions per element); IADD + LOP3 run at 128 lanes/clk.
+__device__ __forceinline__ uint32_t tf32_rna_bits(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
+
 // 4 fp32 -> 4 tf32 "hi" (round to nearest) + 4 tf32 "lo" (rn of the exact remainder)
 __device__ __forceinline__ void split4_tf32(float4 x, uint4& hi, uint4& lo) {
     const float v[4] = {x.x, x.y, x.z, x.w};
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h[i]) : "f"(v[i]));
-        const float r = v[i] - __uint_as_float(h[i]);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l[i]) : "f"(r));
+        h[i] = tf32_rna_bits(v[i]);
+        l[i] = tf32_rna_bits(v[i] - __uint_as_float(h[i]));
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
