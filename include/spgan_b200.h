@@ -184,6 +184,12 @@ int spgan_segmax_gather(const float *x, const int32_t *arg, int64_t R, int C, in
  * Generator.py:79) and its backward dx = y * (g - sum_k g*y). */
 int spgan_softmax_k(const float *x, int64_t P, int k, int C, float *y, spgan_stream_t stream);
 int spgan_softmax_k_bwd(const float *g, const float *y, int64_t P, int k, int C, float *dx, spgan_stream_t stream);
+/* Fused attention modulation of EdgeBlock (Generator.py:79,82): w = softmax_k(x), prod = y * w, and its
+ * backward dx = w (g y - sum_k g y w), dy = g w (dx / dy may be NULL). */
+int spgan_softmax_mul_k(const float *x, const float *y, int64_t P, int k, int C, float *w, float *prod,
+                        spgan_stream_t stream);
+int spgan_softmax_mul_k_bwd(const float *g, const float *y, const float *w, int64_t P, int k, int C, float *dx,
+                            float *dy, spgan_stream_t stream);
 
 /* ------------------------------------------------------------------ edge aggregation
  * out[(p*k + r), :] = (pc ? pc[p,:] : 0) + pn[j,:] - pn[p,:] + bias, j = b(p)*N + idx[p, r]:

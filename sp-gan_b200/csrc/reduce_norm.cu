@@ -502,6 +502,48 @@ __global__ void softmax_k_bwd_kernel(const float* __restrict__ g, const float* _
         }
     }
 }
+// prod = y * softmax_k(x) (EdgeBlock: Generator.py:79,82) in one pass; w = softmax is kept for the backward
+__global__ void softmax_mul_k_kernel(const float* __restrict__ x, const float* __restrict__ yv, int64_t P, int k, int C,
+                                     float* __restrict__ w, float* __restrict__ prod) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const int64_t o = p * k * C + c;
+        float m = -FLT_MAX;
+        for (int r = 0; r < k; ++r) m = fmaxf(m, __ldg(x + o + (int64_t)r * C));
+        float s = 0.f;
+        for (int r = 0; r < k; ++r) s += expf(__ldg(x + o + (int64_t)r * C) - m);
+        const float inv = 1.f / s;
+        for (int r = 0; r < k; ++r) {
+            const float wr = expf(__ldg(x + o + (int64_t)r * C) - m) * inv;
+            w[o + (int64_t)r * C] = wr;
+            prod[o + (int64_t)r * C] = wr * __ldg(yv + o + (int64_t)r * C);
+        }
+    }
+}
+// backward of prod = y * w, w = softmax_k(x): dy = g w, dx = w (g y - sum_r g y w)
+__global__ void softmax_mul_k_bwd_kernel(const float* __restrict__ g, const float* __restrict__ yv,
+                                         const float* __restrict__ w, int64_t P, int k, int C, float* __restrict__ dx,
+                                         float* __restrict__ dy) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const int64_t o = p * k * C + c;
+        float s = 0.f;
+        for (int r = 0; r < k; ++r) {
+            const int64_t a = o + (int64_t)r * C;
+            s = fmaf(__ldg(g + a) * __ldg(yv + a), __ldg(w + a), s);
+        }
+        for (int r = 0; r < k; ++r) {
+            const int64_t a = o + (int64_t)r * C;
+            const float gr = __ldg(g + a), wr = __ldg(w + a);
+            if (dx) dx[a] = wr * (gr * __ldg(yv + a) - s);
+            if (dy) dy[a] = gr * wr;
+        }
+    }
+}
 __global__ void kmax_kernel(const float* __restrict__ x, int64_t P, int k, int C, float* __restrict__ out,
                             int32_t* __restrict__ arg) {
     const int64_t total = P * C;
@@ -821,6 +863,20 @@ extern "C" int spgan_softmax_k_bwd(const float* g, const float* y, int64_t P, in
     SPGAN_CHECK_ARG(g && y && dx && P >= 0 && k >= 1 && C >= 1);
     if (P == 0) return SPGAN_OK;
     softmax_k_bwd_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(g, y, P, k, C, dx);
+    return spgan_launch_status();
+}
+extern "C" int spgan_softmax_mul_k(const float* x, const float* y, int64_t P, int k, int C, float* w, float* prod,
+                                   spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && y && w && prod && P >= 0 && k >= 1 && C >= 1);
+    if (P == 0) return SPGAN_OK;
+    softmax_mul_k_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(x, y, P, k, C, w, prod);
+    return spgan_launch_status();
+}
+extern "C" int spgan_softmax_mul_k_bwd(const float* g, const float* y, const float* w, int64_t P, int k, int C,
+                                       float* dx, float* dy, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && y && w && P >= 0 && k >= 1 && C >= 1);
+    if (P == 0) return SPGAN_OK;
+    softmax_mul_k_bwd_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(g, y, w, P, k, C, dx, dy);
     return spgan_launch_status();
 }
 extern "C" int spgan_kmax(const float* x, int64_t P, int k, int C, float* out, int32_t* arg, spgan_stream_t s) {

@@ -70,7 +70,7 @@ class edgeConv(nn.Module, _KnnMixin):
         C, F = self.Fin, self.Fout
         W = self.conv.conv.weight.view(F, 2 * C)
         a = ops.linear(x_rows, W[:, :C])                  # centre half, per point
-        d = ops.linear(x_rows, W[:, C:])                  # difference half, per point
+        d = ops.linear(x_rows, W[:, C:], engine=0)        # difference half, per point (differenced: exact fp32)
         y = ops.EdgeCombine.apply(a, d, self.conv.conv.bias, idx32, N, self.k)
         y = ops.batch_norm_act(y, self.conv.bn, 0.0)
         return ops.KMax.apply(y, self.k)
@@ -104,19 +104,18 @@ class EdgeBlock(nn.Module, _KnnMixin):
         cw0, bw0, _, cw1, bw1, _ = self.conv_w
         cx, bx, _ = self.conv_x
         # conv_w on the difference half: W (x_j - x_i) + b == (W x)_j - (W x)_i + b
-        p1 = ops.linear(x_rows, cw0.weight)
+        p1 = ops.linear(x_rows, cw0.weight, engine=0)          # differenced below: exact fp32 products
         w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k)             # [P*k, F/2]
         w = ops.batch_norm_act(w, bw0, NEG)
         w = ops.linear(w, cw1.weight, cw1.bias)                                  # [P*k, F]
         w = ops.batch_norm_act(w, bw1, NEG)
-        w = ops.SoftmaxK.apply(w, k)
         # conv_x on [centre, difference]
         Wx = cx.weight.view(F, 2 * C)
         a = ops.linear(x_rows, Wx[:, :C])
-        d = ops.linear(x_rows, Wx[:, C:])
+        d = ops.linear(x_rows, Wx[:, C:], engine=0)
         y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k)
         y = ops.batch_norm_act(y, bx, NEG)
-        y = ops.Mul.apply(y, w)
+        y = ops.SoftmaxMulK.apply(w, y, k)                                      # softmax over k, then y * w
         # conv_out: kernel [1, k] == one dense contraction over (neighbour, channel)
         Wo = ops.PermuteOCK.apply(self.conv_out.weight)                         # [F, k*F]
         return ops.Gemm.apply(y.view(P, k * F), Wo, self.conv_out.bias, False, True)

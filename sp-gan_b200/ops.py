@@ -167,14 +167,16 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
 
 
 class Gemm(Function):
-    """C = op(A) @ op(B) + bias.  Closed under differentiation (backward = three Gemm/ColSum)."""
+    """C = op(A) @ op(B) + bias.  Closed under differentiation (backward = three Gemm/ColSum).
+    `engine` (None = module default) pins the arithmetic of the FORWARD product only: the per-point
+    projections that EdgeCombine differences (pn[j] - pn[p]) use engine 0 (exact fp32 FMA chains)."""
 
     @staticmethod
-    def forward(ctx, A, B, bias, ta, tb):
+    def forward(ctx, A, B, bias, ta, tb, engine=None):
         ctx.ta, ctx.tb = ta, tb
         ctx.save_for_backward(A, B)
         ctx.has_bias = bias is not None
-        return gemm_raw(A, B, bias, ta, tb)
+        return gemm_raw(A, B, bias, ta, tb, engine=engine)
 
     @staticmethod
     def backward(ctx, g):
@@ -189,13 +191,13 @@ class Gemm(Function):
             dB = Gemm.apply(A, g, None, not ta, False) if not tb else Gemm.apply(g, A, None, True, ta)
         if ctx.has_bias and ctx.needs_input_grad[2] and params_too:
             db = ColSum.apply(g, g.shape[0]).view(-1)
-        return dA, dB, db, None, None
+        return dA, dB, db, None, None, None
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, engine=None):
     """x [R, Cin] @ weight[Cout, Cin(,1(,1))]^T + bias -- Conv1d(k=1) / Conv2d(1x1) / Linear."""
     w = weight.reshape(weight.shape[0], -1) if weight.dim() != 2 else weight
-    return Gemm.apply(x, w, bias, False, True)
+    return Gemm.apply(x, w, bias, False, True, engine)
 
 
 # =========================================================================================
@@ -758,6 +760,35 @@ class SoftmaxK(Function):
         dx = torch.empty_like(y)
         L().softmax_k_bwd(g.data_ptr(), y.data_ptr(), E // ctx.k, ctx.k, C, dx.data_ptr(), _stream())
         return dx, None
+
+
+class SoftmaxMulK(Function):
+    """y * softmax_k(x) in one pass (EdgeBlock's attention modulation, Generator.py:79,82); x, y are
+    [P*k, C] edge-major.  First-order only."""
+
+    @staticmethod
+    def forward(ctx, x, y, k):
+        x, y = _c(_rows2d(x)), _c(_rows2d(y))
+        E, C = x.shape
+        w = torch.empty_like(x)
+        prod = torch.empty_like(x)
+        L().softmax_mul_k(x.data_ptr(), y.data_ptr(), E // k, k, C, w.data_ptr(), prod.data_ptr(), _stream())
+        ctx.k = k
+        ctx.save_for_backward(y, w)
+        return prod
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        y, w = ctx.saved_tensors
+        g = _c(g)
+        E, C = y.shape
+        dx = torch.empty_like(y) if ctx.needs_input_grad[0] else None
+        dy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        L().softmax_mul_k_bwd(g.data_ptr(), y.data_ptr(), w.data_ptr(), E // ctx.k, ctx.k, C,
+                              dx.data_ptr() if dx is not None else None, dy.data_ptr() if dy is not None else None,
+                              _stream())
+        return dx, dy, None
 
 
 class KMax(Function):

@@ -307,6 +307,21 @@ def test_softmax_k_and_kmax():
     close(x.grad, xr.grad, 0.0)
 
 
+def test_softmax_mul_k_fused():
+    ops = _ops()
+    P, k, C = 200, 10, 64
+    x0, y0, r = rnd(P * k, C, seed=71), rnd(P * k, C, seed=72), rnd(P * k, C, seed=73)
+    xr, yr = x0.clone().requires_grad_(), y0.clone().requires_grad_()
+    ref = yr * torch.softmax(xr.view(P, k, C), 1).view(P * k, C)
+    (ref * r).sum().backward()
+    x, y = x0.cuda().requires_grad_(), y0.cuda().requires_grad_()
+    out = ops.SoftmaxMulK.apply(x, y, k)
+    close(out, ref, 1e-5)
+    ops.MeanScale.apply(ops.Mul.apply(out, r.cuda()), float(r.numel())).backward()
+    close(x.grad, xr.grad, 1e-4)
+    close(y.grad, yr.grad, 1e-5)
+
+
 @pytest.mark.parametrize("C", [64, 3, 30])
 def test_edge_combine_forward_backward(C):
     ops = _ops()
