@@ -233,10 +233,13 @@ def main():
 
     # ---- per-kernel device times of one more step (CUDA events around every C-ABI launch)
     roofline, kernel_share = None, None
-    if rank == 0 and not minimal:
-        L.profile = []
+    if not minimal:
+        # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 records it
+        if rank == 0:
+            L.profile = []
         step_on(resident[0])
         torch.cuda.synchronize()
+    if rank == 0 and not minimal:
         prof, L.profile = L.profile, None
         agg = {}
         for name, ia, s, e in prof:
