@@ -232,7 +232,7 @@ def main():
            "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps}
 
     # ---- per-kernel device times of one more step (CUDA events around every C-ABI launch)
-    roofline, kernel_share = None, None
+    roofline, kernel_share, roofline_all, roofline_knn = None, None, None, None
     if not minimal:
         # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 records it
         if rank == 0:
@@ -269,15 +269,86 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        def peak_tf():
+            return peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s"
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1.json")))
+        except OSError:
+            ncu = {}
+        # dominant kernel: the tcgen05 GEMM on its biggest shape, the critic's fc2 forward
+        # (NT, M = B*N points, N = 1024, K = 256); algorithmic FLOPs per launch = 2*M*N*K
+        dom = [(ia, s_.elapsed_time(e_)) for name, ia, s_, e_ in prof
+               if name == "spgan_gemm" and ia[0] == 0 and ia[1] == 1 and ia[3] == 1024 and ia[4] == 256]
         g = agg.get("spgan_gemm")
+        if dom and pkg.ops.GEMM_ENGINE in (1, 2):
+            t_ms = sum(t for _, t in dom) / len(dom)
+            fl = gemm_flops(dom[0][0])
+            ach = fl / (t_ms / 1e3) / 1e12
+            cap = ncu.get("gemm_tc_kernel<128, 1>", {})
+            roofline = {"kernel": "gemm_tc_kernel<128,TF32x3> (tcgen05), critic fc2 forward M=%d N=1024 K=256" % dom[0][0][2],
+                        "bound": "tensor", "achieved": ach, "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(),
+                        "traffic": cap.get("dram_traffic_bytes"), "traffic_source": "profiles/ncu_r1.json (ncu --set full, same shape)",
+                        "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 4.0 * dom[0][0][2] * (1024 + 256),
+                        "launches_per_step": len(dom), "avg_launch_ms": t_ms,
+                        "share_of_step": sum(t for _, t in dom) / total,
+                        "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_pct"),
+                        "note": "fp32-faithful TF32x3: 3 tcgen05 MMAs per product at half the bf16 rate, so the attainable "
+                                "fraction of the bf16 peak is 1/6 = 0.167",
+                        "peak_source": peak_src}
         if g:
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
             ach = g[2] / (g[0] / 1e3) / 1e12
-            roofline = {"kernel": "spgan_gemm (%s)" % ("tcgen05" if pkg.ops.GEMM_ENGINE == 1 else "fp32 CUDA cores"),
-                        "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": None, "launches_per_step": g[1], "avg_launch_ms": g[0] / g[1],
-                        "share_of_step": g[0] / total,
-                        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s"}
+            roofline_all = {"kernel": "spgan_gemm, all %d launches of the step" % g[1], "bound": "tensor", "achieved": ach,
+                            "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(), "share_of_step": g[0] / total}
+            if roofline is None:
+                roofline = dict(roofline_all, traffic=None, peak_source=peak_src)
+        else:
+            roofline_all = None
+        kn = [(ia, s_.elapsed_time(e_)) for name, ia, s_, e_ in prof if name == "spgan_knn_group"]
+        roofline_knn = None
+        if kn:
+            ia, t_ms = max(kn, key=lambda kv: kv[0][1])              # (B, C, N, k): the C = 64 launch
+            Bk, Ck, Nk, kk = ia[0], ia[1], ia[2], ia[3]
+            fl = 2.0 * Bk * Nk * Nk * Ck
+            byts = 4.0 * (Bk * Ck * Nk + Bk * Nk * kk)
+            ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            roofline_knn = {"kernel": "knn_group_fast_kernel B=%d C=%d N=%d k=%d (bit-exact fp32 recipe: CUDA cores only)" % (Bk, Ck, Nk, kk),
+                            "bound": "fp32 FFMA + selection", "ms": t_ms, "achieved": fl / (t_ms / 1e3) / 1e12,
+                            "peak": ffma_peak, "unit": "TFLOP/s", "frac": fl / (t_ms / 1e3) / 1e12 / ffma_peak,
+                            "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                            "hbm_algorithmic_bytes": byts, "hbm_gbs": byts / (t_ms / 1e3) / 1e9,
+                            "hbm_frac_of_measured": byts / (t_ms / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                            "traffic": ncu.get("knn_group_fast_kernel", {}).get("dram_traffic_bytes")}
+
+    # ---- sub-metrics of BASELINE's metric string: "kNN+EdgeConv ms/batch" and configs[1] (generator forward only)
+    sub = None
+    if rank == 0 and not minimal:
+        def ev_ms(fn, reps=5):
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return sorted(ts)[len(ts) // 2]
+        d0 = resident[0]
+        with torch.no_grad():
+            z = d0["z_d"].expand(B, N, NZ)
+            g_fwd = ev_ms(lambda: G(x, z))
+            x1 = G._last_x1                                                  # EdgeConv2's input rows [B*N, 64]
+            x1_bcn = pkg.ops.RowsToBcn.apply(x1, B, x1.shape[1], N)
+            pc_rows = x.reshape(B * N, 3)
+            pc_bcn = pkg.ops.RowsToBcn.apply(pc_rows, B, 3, N)
+            knn2 = ev_ms(lambda: pkg.ops.knn_indices(x1_bcn, G.nk))
+            knn1 = ev_ms(lambda: pkg.ops.knn_indices(pc_bcn, G.nk))
+            idx2 = pkg.ops.knn_indices(x1_bcn, G.nk)
+            idx1 = pkg.ops.knn_indices(pc_bcn, G.nk)
+            ec2 = ev_ms(lambda: G.EdgeConv2.forward_rows(x1, idx2, B, N))
+            ec1 = ev_ms(lambda: G.EdgeConv1.forward_rows(pc_rows, idx1, B, N))
+        sub = {"generator_forward_ms_per_batch": g_fwd, "generator_forward_clouds_per_s": B / (g_fwd / 1e3),
+               "knn_edgeconv_ms_per_batch": knn1 + knn2 + ec1 + ec2,
+               "knn_C3_ms": knn1, "knn_C64_ms": knn2, "edgeblock1_fwd_ms": ec1, "edgeblock2_fwd_ms": ec2,
+               "note": "forward, train-mode BN, B=%d N=%d k=%d; the C=3 graph of the static sphere is cached inside "
+                       "training steps (model.py:231) but counted here" % (B, N, G.nk)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -295,6 +366,7 @@ def main():
                            "sphere": ball_src, "gemm_engine": pkg.ops.GEMM_ENGINE,
                            "l2": "no flush needed: per-step working set (activations) is several GB >> 126 MB L2"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "roofline_all_gemm": roofline_all, "roofline_knn": roofline_knn, "submetrics": sub,
                 "kernel_share": kernel_share, "cpu_baseline": cpu_baseline,
                 "last_losses": losses[-1] if losses else None}
         print(json.dumps(line), flush=True)

@@ -180,10 +180,42 @@ int spgan_segmax_scatter(const float *g, const int32_t *arg, int64_t R, int C, i
 /* out[s,c] = x[s*seg_rows + arg[s,c], c] */
 int spgan_segmax_gather(const float *x, const int32_t *arg, int64_t R, int C, int64_t seg_rows, float *out,
                         spgan_stream_t stream);
+/* Fused train-mode BatchNorm1d + LeakyReLU(slope > 0) + max over the points of every cloud, the tail of the critic's
+ * point-wise stack (Generation/Discriminator.py:77-81,104).  x [R, C] is read once: column moments over all R rows
+ * (mean, rstd, biased var as spgan_colstats with seg_rows = R) and, per segment of seg_rows rows, the pooled value
+ * pooled[s,c] = max_r lrelu(bn(x[r,c])) with arg[s,c] = row (inside the segment) of the first extreme of x[:,c]
+ * (maximum for gamma >= 0, minimum for gamma < 0: every fp32 step of bn + lrelu is monotone).  C % 4 == 0.
+ * workspace: >= spgan_bn_pool_workspace(R, C, seg_rows) bytes, 16-byte aligned. */
+size_t spgan_bn_pool_workspace(int64_t R, int C, int64_t seg_rows);
+int spgan_bn_pool_fwd(const float *x, int64_t R, int C, int64_t seg_rows, const float *gamma, const float *beta,
+                      float eps, float slope, float *mean, float *rstd, float *var, float *pooled, int32_t *arg,
+                      void *workspace, spgan_stream_t stream);
+/* Backward of spgan_bn_pool_fwd for a gradient gpooled [nseg, C]: gprime [nseg, C] (scratch: gradient at the
+ * pre-activation of the selected rows), sg[c] = sum gprime (= d beta), sgx[c] = sum gprime * xhat (= d gamma),
+ * dx [R, C] = gamma rstd (gprime at the selected row - sg / R - xhat sgx / R); dx may be NULL. */
+int spgan_bn_pool_bwd(const float *gpooled, const float *x, const int32_t *arg, int64_t R, int C, int64_t seg_rows,
+                      const float *mean, const float *rstd, const float *gamma, const float *beta, float slope,
+                      float *gprime, float *sg, float *sgx, float *dx, spgan_stream_t stream);
 /* softmax over the k neighbours of each (point, channel): x, y are [P, k, C] (F.softmax(w, -1),
  * Generator.py:79) and its backward dx = y * (g - sum_k g*y). */
 int spgan_softmax_k(const float *x, int64_t P, int k, int C, float *y, spgan_stream_t stream);
 int spgan_softmax_k_bwd(const float *g, const float *y, int64_t P, int k, int C, float *dx, spgan_stream_t stream);
+/* The same with both train-mode BatchNorm + LeakyReLU applications folded into the loads (Generator.py:78-82):
+ * w = softmax_k(lrelu(bn_w(xw))), prod = lrelu(bn_y(xy)) * w from the PRE-normalisation tensors xw, xy [P, k, C]
+ * and per-channel (mean, rstd, gamma, beta) of the two BatchNorm2d layers; bit-identical to
+ * spgan_norm_apply x2 + spgan_softmax_mul_k without writing the normalised tensors.  k <= 16.
+ * Backward: dwa / dya = gradients w.r.t. the two ACTIVATED tensors (feed spgan_norm_bwd_*); either may be NULL. */
+int spgan_bn_softmax_mul_k(const float *xw, const float *xy, int64_t P, int k, int C, const float *mean_w,
+                           const float *rstd_w, const float *gamma_w, const float *beta_w, const float *mean_y,
+                           const float *rstd_y, const float *gamma_y, const float *beta_y, float slope, float *w,
+                           float *prod, spgan_stream_t stream);
+int spgan_bn_softmax_mul_k_bwd(const float *g, const float *xy, const float *w, int64_t P, int k, int C,
+                               const float *mean_y, const float *rstd_y, const float *gamma_y, const float *beta_y,
+                               float slope, float *dwa, float *dya, spgan_stream_t stream);
+/* Row softmax y[r,:] = softmax(x[r,:]) over the last axis of [R, N] and its backward dx = y * (g - sum_j g_j y_j):
+ * the N x N attention map of the optional Attention block (--attn; Generation/modules.py:549-553). */
+int spgan_row_softmax(const float *x, int64_t R, int N, float *y, spgan_stream_t stream);
+int spgan_row_softmax_bwd(const float *g, const float *y, int64_t R, int N, float *dx, spgan_stream_t stream);
 /* Fused attention modulation of EdgeBlock (Generator.py:79,82): w = softmax_k(x), prod = y * w, and its
  * backward dx = w (g y - sum_k g y w), dy = g w (dx / dy may be NULL). */
 int spgan_softmax_mul_k(const float *x, const float *y, int64_t P, int k, int C, float *w, float *prod,

@@ -73,20 +73,32 @@ def edge_conv_spec(prefix, fin, fout):
     return _conv(p + "conv.conv", (fout, 2 * fin, 1, 1)) + _bn(p + "conv.bn", fout)
 
 
+def _eq_conv(prefix, shape, eql, inner):
+    """nn.Conv1d / nn.Linear keys, or the EqualConv1d / EqualLinear ones (modules.py:202-243, 256-272):
+    <prefix>.<inner>.weight_orig ~ N(0,1) (kind "w1") and <prefix>.<inner>.bias."""
+    if not eql:
+        return _conv(prefix, shape)
+    return [(prefix + "." + inner + ".weight_orig", tuple(shape), "w1"), (prefix + "." + inner + ".bias", (shape[0],), "b")]
+
+
 def generator_spec(opts):
     """Key order follows module registration order in Generator.__init__ (Generator.py:92-156)."""
-    if opts.eql or opts.attn:
-        raise NotImplementedError("oracle spec covers the default flags plus use_head/off/z_norm")
     dim, k = 128, opts.nk // 2
+    eql = bool(opts.eql)
     s = []
-    s += _conv("head.0", (dim, 3 + opts.nz, 1)) + _conv("head.2", (dim, dim, 1))
-    s += _conv("global_conv.0", (dim, dim))[:1] + [("global_conv.0.bias", (dim,), "b")]
+    s += _eq_conv("head.0", (dim, 3 + opts.nz, 1), eql, "conv") + _eq_conv("head.2", (dim, dim, 1), eql, "conv")
+    if opts.attn:                                              # Attention(640), modules.py:534-546
+        ch = dim + 512
+        s += [("attn.gamma", (), "gain"), ("attn.theta.weight", (ch // 8, ch, 1), "w"),
+              ("attn.phi.weight", (ch // 8, ch, 1), "w"), ("attn.g.weight", (ch // 2, ch, 1), "w"),
+              ("attn.o.weight", (ch, ch // 2, 1), "w")]
+    s += _eq_conv("global_conv.0", (dim, dim), eql, "linear")
     s += _bn("global_conv.1", dim)
-    s += [("global_conv.3.weight", (512, dim), "w"), ("global_conv.3.bias", (512,), "b")]
+    s += _eq_conv("global_conv.3", (512, dim), eql, "linear")
     s += _bn("global_conv.4", 512)
     s += _conv("tail.0", (256, 512 + dim, 1)) + _conv("tail.2", (64, 256, 1)) + _conv("tail.4", (3, 64, 1))
     if opts.use_head:
-        s += _conv("pc_head.0", (dim // 2, 3, 1)) + _conv("pc_head.2", (dim, dim // 2, 1))
+        s += _eq_conv("pc_head.0", (dim // 2, 3, 1), eql, "conv") + _eq_conv("pc_head.2", (dim, dim // 2, 1), eql, "conv")
         s += edge_block_spec("EdgeConv1", dim, dim, k)
         s += _conv("adain1.style", (2 * dim, dim, 1))
         s += edge_block_spec("EdgeConv2", dim, dim, k)
@@ -126,6 +138,10 @@ def synth_state(spec, seed):
         if kind == "w":
             fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else 1
             v = rng.standard_normal(shape) * (1.0 / math.sqrt(fan_in))
+        elif kind == "w1":                      # equalised-lr weight_orig: unit normal, scaled at use
+            v = rng.standard_normal(shape)
+        elif kind == "gain":                    # Attention.gamma (0 at init; non-zero here to exercise the block)
+            v = np.asarray(0.5)
         elif kind == "b":
             v = 0.1 * rng.standard_normal(shape)
         elif kind == "bn_w":
@@ -220,12 +236,32 @@ def adaptive_point_norm(sd, x, style):
     return gamma * F.instance_norm(x, eps=IN_EPS) + beta
 
 
+def _wb(sd, prefix, opts, inner):
+    """(weight, bias) of a Conv1d / Linear, or of its equalised-lr variant: weight_orig * sqrt(2 / fan_in)
+    with fan_in = in_channels * kernel elements (modules.py:256-262)."""
+    if not opts.eql:
+        return sd[prefix + ".weight"], sd[prefix + ".bias"]
+    w = sd[prefix + "." + inner + ".weight_orig"]
+    fan_in = w.size(1) * w[0][0].numel()
+    return w * math.sqrt(2.0 / fan_in), sd[prefix + "." + inner + ".bias"]
+
+
+def attention(sd, x):
+    """Attention.forward (modules.py:548-558) on x [B, ch, N]."""
+    theta = F.conv1d(x, sd["theta.weight"])
+    phi = F.conv1d(x, sd["phi.weight"])
+    g = F.conv1d(x, sd["g.weight"])
+    beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)
+    o = F.conv1d(torch.bmm(g, beta.transpose(1, 2)), sd["o.weight"])
+    return sd["gamma"] * o + x
+
+
 def _head(sd, x, z, opts):
     if opts.z_norm:
         z = z / (z.norm(p=2, dim=-1, keepdim=True) + 1e-8)
     s = torch.cat([x, z], dim=-1).transpose(2, 1).contiguous()
-    s = F.leaky_relu(F.conv1d(s, sd["head.0.weight"], sd["head.0.bias"]), NEG_SLOPE)
-    return F.leaky_relu(F.conv1d(s, sd["head.2.weight"], sd["head.2.bias"]), NEG_SLOPE)
+    s = F.leaky_relu(F.conv1d(s, *_wb(sd, "head.0", opts, "conv")), NEG_SLOPE)
+    return F.leaky_relu(F.conv1d(s, *_wb(sd, "head.2", opts, "conv")), NEG_SLOPE)
 
 
 def _generator_body(sd, x, style, opts, training, idx1=None, idx2=None):
@@ -234,18 +270,20 @@ def _generator_body(sd, x, style, opts, training, idx1=None, idx2=None):
     k = opts.nk // 2
     pc = x.transpose(2, 1).contiguous()
     if opts.use_head:
-        pc = F.leaky_relu(F.conv1d(pc, sd["pc_head.0.weight"], sd["pc_head.0.bias"]), 0.01)
-        pc = F.leaky_relu(F.conv1d(pc, sd["pc_head.2.weight"], sd["pc_head.2.bias"]), 0.01)
+        pc = F.leaky_relu(F.conv1d(pc, *_wb(sd, "pc_head.0", opts, "conv")), 0.01)
+        pc = F.leaky_relu(F.conv1d(pc, *_wb(sd, "pc_head.2", opts, "conv")), 0.01)
     x1 = edge_block(sub_state_view(sd, "EdgeConv1"), pc, k, training, idx1)
     x1 = adaptive_point_norm(sub_state_view(sd, "adain1"), F.leaky_relu(x1, NEG_SLOPE_2), style)
     x2 = edge_block(sub_state_view(sd, "EdgeConv2"), x1, k, training, idx2)
     x2 = adaptive_point_norm(sub_state_view(sd, "adain2"), F.leaky_relu(x2, NEG_SLOPE_2), style)
     g = x2.max(dim=2)[0]
-    g = F.linear(g, sd["global_conv.0.weight"], sd["global_conv.0.bias"])
+    g = F.linear(g, *_wb(sd, "global_conv.0", opts, "linear"))
     g = F.leaky_relu(_batch_norm(g, sd, "global_conv.1", training), NEG_SLOPE)
-    g = F.linear(g, sd["global_conv.3.weight"], sd["global_conv.3.bias"])
+    g = F.linear(g, *_wb(sd, "global_conv.3", opts, "linear"))
     g = F.leaky_relu(_batch_norm(g, sd, "global_conv.4", training), NEG_SLOPE)
     feat = torch.cat([g.unsqueeze(2).expand(B, g.shape[1], N), x2], dim=1)
+    if opts.attn:
+        feat = attention(sub_state_view(sd, "attn"), feat)
     t = F.leaky_relu(F.conv1d(feat, sd["tail.0.weight"], sd["tail.0.bias"]), NEG_SLOPE)
     t = F.leaky_relu(F.conv1d(t, sd["tail.2.weight"], sd["tail.2.bias"]), NEG_SLOPE)
     out = torch.tanh(F.conv1d(t, sd["tail.4.weight"], sd["tail.4.bias"]))

@@ -62,26 +62,54 @@ colreduce_partial_kernel(Op op, int C, int64_t seg_rows, int chunks, int64_t row
 }
 
 template <int NV, typename Fin>
-__global__ void colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
-    // one warp per (segment, column): lanes stride over the row chunks, double-precision combine
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(256)
+colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
+    // block = 32 columns x 8 chunk lanes of one segment: every partial row is read as one coalesced
+    // 128-byte line per warp; double-precision combine (the chunk order is fixed, so the result is
+    // deterministic)
+    __shared__ double red[8][NV][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    for (int64_t seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
+        double s[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) s[v] = 0.0;
+        if (c < C) {
+            for (int ch = ty; ch < chunks; ch += 8)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s[v] += (double)__ldg(partial + (((seg * chunks) + ch) * NV + v) * C + c);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) red[ty][v][tx] = s[v];
+        __syncthreads();
+        if (ty == 0 && c < C) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double t = red[0][v][tx];
+#pragma unroll
+                for (int y = 1; y < 8; ++y) t += red[y][v][tx];
+                s[v] = t;
+            }
+            fin(seg, c, s);
+        }
+        __syncthreads();
+    }
+}
+
+// few chunks per segment (many short segments): one thread per (segment, column), coalesced over columns
+template <int NV, typename Fin>
+__global__ void colreduce_final_small_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
     const int64_t total = nseg * C;
-    for (int64_t i = warp; i < total; i += nwarps) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t seg = i / C;
         const int c = (int)(i - seg * C);
         double s[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) s[v] = 0.0;
-        for (int ch = lane; ch < chunks; ch += 32)
+        for (int ch = 0; ch < chunks; ++ch)
 #pragma unroll
             for (int v = 0; v < NV; ++v) s[v] += (double)__ldg(partial + (((seg * chunks) + ch) * NV + v) * C + c);
-#pragma unroll
-        for (int v = 0; v < NV; ++v)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_xor_sync(0xffffffffu, s[v], o);
-        if (lane == 0) fin(seg, c, s);
+        fin(seg, c, s);
     }
 }
 
@@ -113,7 +141,10 @@ int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStrea
         colreduce_partial_kernel<NV><<<grid, block, 0, st>>>(op, C, seg_rows, p.chunks, p.rows_per_chunk, partial);
         nseg = p.nseg; chunks = p.chunks;
     }
-    colreduce_final_kernel<NV><<<ew_grid(nseg * C * 32, 256), 256, 0, st>>>(partial, C, nseg, chunks, fin);
+    if (chunks <= 8)
+        colreduce_final_small_kernel<NV><<<ew_grid(nseg * C, 256), 256, 0, st>>>(partial, C, nseg, chunks, fin);
+    else
+        colreduce_final_kernel<NV><<<dim3((unsigned)((C + 31) / 32), (unsigned)(nseg < 4096 ? nseg : 4096)), 256, 0, st>>>(partial, C, nseg, chunks, fin);
     return spgan_launch_status();
 }
 
@@ -523,6 +554,75 @@ __global__ void softmax_mul_k_kernel(const float* __restrict__ x, const float* _
     }
 }
 // backward of prod = y * w, w = softmax_k(x): dy = g w, dx = w (g y - sum_r g y w)
+// EdgeBlock attention with both train-mode BatchNorm + LeakyReLU applications folded into the loads
+// (Generator.py:78-82: w = softmax_k(lrelu(bn(xw))), prod = lrelu(bn(xy)) * w).  Same fp32 operation order
+// as norm_apply followed by softmax_mul_k, so the results are bit-identical to the unfused chain; the two
+// normalised [E, C] tensors are never written.  k <= KMAXR values per thread stay in registers.
+constexpr int KMAXR = 16;
+struct BnCol { const float* mean; const float* rstd; const float* gamma; const float* beta; };
+__device__ __forceinline__ float bn_act(float x, float m, float r, float g, float b, float slope) {
+    return lrelu_f(fmaf((x - m) * r, g, b), slope);
+}
+__global__ void __launch_bounds__(256)
+bn_softmax_mul_k_kernel(const float* __restrict__ xw, const float* __restrict__ xy, int64_t P, int k, int C, BnCol bw,
+                        BnCol by, float slope, float* __restrict__ w, float* __restrict__ prod) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const int64_t o = p * k * C + c;
+        const float mw = __ldg(bw.mean + c), rw = __ldg(bw.rstd + c), gw = __ldg(bw.gamma + c), bbw = __ldg(bw.beta + c);
+        const float my = __ldg(by.mean + c), ry = __ldg(by.rstd + c), gy = __ldg(by.gamma + c), bby = __ldg(by.beta + c);
+        float a[KMAXR];
+        float m = -FLT_MAX;
+#pragma unroll
+        for (int r = 0; r < KMAXR; ++r)
+            if (r < k) { a[r] = bn_act(__ldg(xw + o + (int64_t)r * C), mw, rw, gw, bbw, slope); m = fmaxf(m, a[r]); }
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < KMAXR; ++r)
+            if (r < k) { a[r] = expf(a[r] - m); s += a[r]; }
+        const float inv = 1.f / s;
+#pragma unroll
+        for (int r = 0; r < KMAXR; ++r)
+            if (r < k) {
+                const float wr = a[r] * inv;
+                w[o + (int64_t)r * C] = wr;
+                prod[o + (int64_t)r * C] = wr * bn_act(__ldg(xy + o + (int64_t)r * C), my, ry, gy, bby, slope);
+            }
+    }
+}
+// backward of the fused forward up to the two activated tensors: dwa = d/d lrelu(bn(xw)), dya = d/d lrelu(bn(xy));
+// lrelu(bn(xy)) is recomputed from xy.
+__global__ void __launch_bounds__(256)
+bn_softmax_mul_k_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xy, const float* __restrict__ w,
+                            int64_t P, int k, int C, BnCol by, float slope, float* __restrict__ dwa,
+                            float* __restrict__ dya) {
+    const int64_t total = P * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / C;
+        const int c = (int)(i - p * C);
+        const int64_t o = p * k * C + c;
+        const float my = __ldg(by.mean + c), ry = __ldg(by.rstd + c), gy = __ldg(by.gamma + c), bby = __ldg(by.beta + c);
+        float gyv[KMAXR], wv[KMAXR];
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < KMAXR; ++r)
+            if (r < k) {
+                const int64_t a = o + (int64_t)r * C;
+                const float gr = __ldg(g + a);
+                wv[r] = __ldg(w + a);
+                gyv[r] = gr * bn_act(__ldg(xy + a), my, ry, gy, bby, slope);
+                s = fmaf(gyv[r], wv[r], s);
+                if (dya) dya[a] = gr * wv[r];
+            }
+        if (dwa) {
+#pragma unroll
+            for (int r = 0; r < KMAXR; ++r)
+                if (r < k) dwa[o + (int64_t)r * C] = wv[r] * (gyv[r] - s);
+        }
+    }
+}
 __global__ void softmax_mul_k_bwd_kernel(const float* __restrict__ g, const float* __restrict__ yv,
                                          const float* __restrict__ w, int64_t P, int k, int C, float* __restrict__ dx,
                                          float* __restrict__ dy) {
@@ -877,6 +977,28 @@ extern "C" int spgan_softmax_mul_k_bwd(const float* g, const float* y, const flo
     SPGAN_CHECK_ARG(g && y && w && P >= 0 && k >= 1 && C >= 1);
     if (P == 0) return SPGAN_OK;
     softmax_mul_k_bwd_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(g, y, w, P, k, C, dx, dy);
+    return spgan_launch_status();
+}
+extern "C" int spgan_bn_softmax_mul_k(const float* xw, const float* xy, int64_t P, int k, int C, const float* mean_w,
+                                      const float* rstd_w, const float* gamma_w, const float* beta_w,
+                                      const float* mean_y, const float* rstd_y, const float* gamma_y,
+                                      const float* beta_y, float slope, float* w, float* prod, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(xw && xy && w && prod && mean_w && rstd_w && gamma_w && beta_w && mean_y && rstd_y && gamma_y && beta_y);
+    SPGAN_CHECK_ARG(P >= 0 && k >= 1 && C >= 1);
+    if (k > KMAXR) return SPGAN_E_UNSUPPORTED;
+    if (P == 0) return SPGAN_OK;
+    bn_softmax_mul_k_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(
+        xw, xy, P, k, C, BnCol{mean_w, rstd_w, gamma_w, beta_w}, BnCol{mean_y, rstd_y, gamma_y, beta_y}, slope, w, prod);
+    return spgan_launch_status();
+}
+extern "C" int spgan_bn_softmax_mul_k_bwd(const float* g, const float* xy, const float* w, int64_t P, int k, int C,
+                                          const float* mean_y, const float* rstd_y, const float* gamma_y,
+                                          const float* beta_y, float slope, float* dwa, float* dya, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && xy && w && mean_y && rstd_y && gamma_y && beta_y && P >= 0 && k >= 1 && C >= 1);
+    if (k > KMAXR) return SPGAN_E_UNSUPPORTED;
+    if (P == 0) return SPGAN_OK;
+    bn_softmax_mul_k_bwd_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(
+        g, xy, w, P, k, C, BnCol{mean_y, rstd_y, gamma_y, beta_y}, slope, dwa, dya);
     return spgan_launch_status();
 }
 extern "C" int spgan_kmax(const float* x, int64_t P, int k, int C, float* out, int32_t* arg, spgan_stream_t s) {

@@ -107,15 +107,14 @@ class EdgeBlock(nn.Module, _KnnMixin):
         p1 = ops.linear(x_rows, cw0.weight, engine=0)          # differenced below: exact fp32 products
         w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k)             # [P*k, F/2]
         w = ops.batch_norm_act(w, bw0, NEG)
-        w = ops.linear(w, cw1.weight, cw1.bias)                                  # [P*k, F]
-        w = ops.batch_norm_act(w, bw1, NEG)
+        w = ops.linear(w, cw1.weight, cw1.bias)                                  # [P*k, F], pre-BN
         # conv_x on [centre, difference]
         Wx = cx.weight.view(F, 2 * C)
         a = ops.linear(x_rows, Wx[:, :C])
         d = ops.linear(x_rows, Wx[:, C:], engine=0)
-        y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k)
-        y = ops.batch_norm_act(y, bx, NEG)
-        y = ops.SoftmaxMulK.apply(w, y, k)                                      # softmax over k, then y * w
+        y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k)                   # [P*k, F], pre-BN
+        # BN + LeakyReLU on both branches, softmax over k, then y * w: one fused pass
+        y = ops.bn_act_softmax_mul_k(w, bw1, y, bx, NEG, k)
         # conv_out: kernel [1, k] == one dense contraction over (neighbour, channel)
         Wo = ops.PermuteOCK.apply(self.conv_out.weight)                         # [F, k*F]
         return ops.Gemm.apply(y.view(P, k * F), Wo, self.conv_out.bias, False, True)

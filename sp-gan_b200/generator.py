@@ -1,4 +1,6 @@
 """AdaptivePointNorm and Generator with the reference API (Generation/Generator.py:24-45, 91-261)."""
+import math
+
 import torch
 import torch.nn as nn
 
@@ -9,13 +11,94 @@ NEG_2 = 0.2          # Generator.py:22
 IN_EPS = 1e-5
 
 
+class _EqualLR(nn.Module):
+    """Equalised-learning-rate holder (modules.py:202-288): the wrapped layer keeps `weight_orig` (and `bias`)
+    as parameters -- same state_dict keys as the reference's EqualConv1d / EqualLinear -- and the weight used
+    is weight_orig * sqrt(2 / fan_in), rebuilt (differentiably) at every use like the reference's
+    forward-pre-hook does."""
+
+    def _wrap(self, layer):
+        layer.weight.data.normal_()
+        layer.bias.data.zero_()
+        w = layer.weight
+        del layer._parameters["weight"]
+        layer.register_parameter("weight_orig", nn.Parameter(w.data))
+        fan_in = w.data.size(1) * w.data[0][0].numel()            # modules.py:259
+        self._scale = math.sqrt(2.0 / fan_in)
+        return layer
+
+    def _layer(self):
+        raise NotImplementedError
+
+    @property
+    def weight(self):
+        return ops.scale(self._layer().weight_orig, self._scale)
+
+    @property
+    def bias(self):
+        return self._layer().bias
+
+
+class EqualConv1d(_EqualLR):
+    """modules.py:202-213 (parameters: conv.weight_orig, conv.bias)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.conv = self._wrap(nn.Conv1d(*args, **kwargs))
+
+    def _layer(self):
+        return self.conv
+
+
+class EqualLinear(_EqualLR):
+    """modules.py:230-243 (parameters: linear.weight_orig, linear.bias)."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.linear = self._wrap(nn.Linear(in_dim, out_dim))
+
+    def _layer(self):
+        return self.linear
+
+
+class Attention(nn.Module):
+    """Optional N x N self-attention over the 640-channel feature (--attn; modules.py:534-558): parameter
+    holder for theta / phi / g / o (bias-free Conv1d) and the learnable gain gamma; forward_rows composes the
+    same primitives as the rest of the generator (no tuned path: non-default flag)."""
+
+    def __init__(self, ch, name="attention"):
+        super().__init__()
+        self.ch = ch
+        self.theta = nn.Conv1d(ch, ch // 8, 1, bias=False)
+        self.phi = nn.Conv1d(ch, ch // 8, 1, bias=False)
+        self.g = nn.Conv1d(ch, ch // 2, 1, bias=False)
+        self.o = nn.Conv1d(ch // 2, ch, 1, bias=False)
+        self.gamma = nn.Parameter(torch.tensor(0.), requires_grad=True)
+
+    def forward_rows(self, x_rows, B, N):
+        theta = ops.linear(x_rows, self.theta.weight)                        # [B*N, ch/8]
+        phi = ops.linear(x_rows, self.phi.weight)
+        g = ops.linear(x_rows, self.g.weight)                                # [B*N, ch/2]
+        beta = ops.RowSoftmax.apply(ops.SegGemm.apply(theta, phi, B, True))  # softmax_j(theta_i . phi_j), [B*N, N]
+        o = ops.linear(ops.SegGemm.apply(beta, g, B, False), self.o.weight)  # sum_j beta_ij g_j -> [B*N, ch]
+        n = o.numel()
+        gain = ops.BcastSeg.apply(self.gamma.view(1, 1), n, n)               # the scalar gain, differentiable
+        return ops.add(ops.Mul.apply(o.view(n, 1), gain).view(o.shape), x_rows)
+
+    def forward(self, x, y=None):
+        B, C, N = x.shape
+        return ops.RowsToBcn.apply(self.forward_rows(ops.BcnToRows.apply(x), B, N), B, C, N)
+
+
 class AdaptivePointNorm(nn.Module):
     """InstanceNorm1d(input) * gamma + beta with (gamma, beta) = chunk(Conv1d(style)) (Generator.py:24-45)."""
 
     def __init__(self, in_channel, style_dim, use_eql=False):
         super().__init__()
         if use_eql:
-            raise NotImplementedError("--eql (EqualConv1d) is not implemented in spgan_b200 yet")
+            # the reference's own AdaptivePointNorm(use_eql=True) raises AttributeError (Generator.py:32 touches
+            # EqualConv1d.weight before any forward); Generator never passes it (Generator.py:146-153)
+            raise NotImplementedError("AdaptivePointNorm(use_eql=True) is unusable in the reference as well")
         self.in_channel = in_channel
         self.norm = nn.InstanceNorm1d(in_channel)
         self.style = nn.Conv1d(style_dim, in_channel * 2, 1)
@@ -50,25 +133,26 @@ class Generator(nn.Module):
         self.off = opts.off
         self.use_attn = opts.attn
         self.use_head = opts.use_head
-        if getattr(opts, "eql", False):
-            raise NotImplementedError("--eql (EqualConv1d/EqualLinear) is not implemented in spgan_b200 yet")
-        if self.use_attn:
-            raise NotImplementedError("--attn (N x N Attention(640)) is not implemented in spgan_b200 yet")
+        eql = bool(getattr(opts, "eql", False))
+        Conv = EqualConv1d if eql else nn.Conv1d                  # Generator.py:103-104
+        Linear = EqualLinear if eql else nn.Linear
         dim = 128
         self.head = nn.Sequential(
-            nn.Conv1d(3 + self.nz, dim, 1), nn.LeakyReLU(NEG, inplace=True),
-            nn.Conv1d(dim, dim, 1), nn.LeakyReLU(NEG, inplace=True))
+            Conv(3 + self.nz, dim, 1), nn.LeakyReLU(NEG, inplace=True),
+            Conv(dim, dim, 1), nn.LeakyReLU(NEG, inplace=True))
+        if self.use_attn:
+            self.attn = Attention(dim + 512)                      # Generator.py:116-117
         self.global_conv = nn.Sequential(
-            nn.Linear(dim, dim), nn.BatchNorm1d(dim), nn.LeakyReLU(NEG, inplace=True),
-            nn.Linear(dim, 512), nn.BatchNorm1d(512), nn.LeakyReLU(NEG, inplace=True))
+            Linear(dim, dim), nn.BatchNorm1d(dim), nn.LeakyReLU(NEG, inplace=True),
+            Linear(dim, 512), nn.BatchNorm1d(512), nn.LeakyReLU(NEG, inplace=True))
         self.tail = nn.Sequential(
             nn.Conv1d(512 + dim, 256, 1), nn.LeakyReLU(NEG, inplace=True),
             nn.Conv1d(256, 64, 1), nn.LeakyReLU(NEG, inplace=True),
             nn.Conv1d(64, 3, 1), nn.Tanh())
         if self.use_head:
             self.pc_head = nn.Sequential(
-                nn.Conv1d(3, dim // 2, 1), nn.LeakyReLU(inplace=True),
-                nn.Conv1d(dim // 2, dim, 1), nn.LeakyReLU(inplace=True))
+                Conv(3, dim // 2, 1), nn.LeakyReLU(inplace=True),
+                Conv(dim // 2, dim, 1), nn.LeakyReLU(inplace=True))
             self.EdgeConv1 = EdgeBlock(dim, dim, self.nk)
             self.adain1 = AdaptivePointNorm(dim, dim)
             self.EdgeConv2 = EdgeBlock(dim, dim, self.nk)
@@ -136,11 +220,17 @@ class Generator(nn.Module):
         g = ops.batch_norm_act(ops.linear(g, gc[0].weight, gc[0].bias), gc[1], NEG)
         g = ops.batch_norm_act(ops.linear(g, gc[3].weight, gc[3].bias), gc[4], NEG)   # [B, 512]
 
-        # tail[0] over cat(global, x2): the global half is constant per cloud -> per-cloud bias
         W0 = self.tail[0].weight.view(self.tail[0].weight.shape[0], -1)
         ng = g.shape[1]
-        gb = ops.linear(g, W0[:, :ng], self.tail[0].bias)                        # [B, 256]
-        t = ops.AddSegVec.apply(ops.linear(x2, W0[:, ng:]), gb, N)
+        if self.use_attn:
+            # the attention block mixes all 640 channels of cat(global, x2): materialise it (Generator.py:189-192)
+            feat = ops.ConcatCols.apply(ops.BcastSeg.apply(g, B * N, N), x2, N, False)
+            feat = self.attn.forward_rows(feat, B, N)
+            t = ops.linear(feat, W0, self.tail[0].bias)
+        else:
+            # tail[0] over cat(global, x2): the global half is constant per cloud -> per-cloud bias
+            gb = ops.linear(g, W0[:, :ng], self.tail[0].bias)                    # [B, 256]
+            t = ops.AddSegVec.apply(ops.linear(x2, W0[:, ng:]), gb, N)
         t = ops.LRelu.apply(t, NEG)
         t = ops.LRelu.apply(ops.linear(t, self.tail[2].weight, self.tail[2].bias), NEG)
         o = ops.Tanh.apply(ops.linear(t, self.tail[4].weight, self.tail[4].bias))

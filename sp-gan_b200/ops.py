@@ -570,6 +570,63 @@ class BatchNormActTrain(Function):
         return dx, sgx.view(-1), sg.view(-1), None, None
 
 
+class BatchNormActSegMaxTrain(Function):
+    """Fused train-mode BN + LeakyReLU + max over the points of each cloud (the critic's fc2 -> max pool,
+    Discriminator.py:77-81,104): one read of x in the forward, the normalised tensor is never materialised;
+    the backward is sparse in the incoming gradient.  First-order only.
+    Returns (pooled [nseg, C], batch_mean, biased_batch_var)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, slope, seg_rows):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        nseg = R // seg_rows
+        dev = x.device
+        mean = torch.empty((1, C), device=dev, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        var = torch.empty_like(mean)
+        pooled = torch.empty((nseg, C), device=dev, dtype=torch.float32)
+        arg = torch.empty((nseg, C), device=dev, dtype=torch.int32)
+        ws = torch.empty((L().bn_pool_workspace(R, C, seg_rows) + 15) // 16 * 4, device=dev, dtype=torch.float32)
+        L().bn_pool_fwd(x.data_ptr(), R, C, seg_rows, gamma.data_ptr(), beta.data_ptr(), eps, slope, mean.data_ptr(),
+                        rstd.data_ptr(), var.data_ptr(), pooled.data_ptr(), arg.data_ptr(), ws.data_ptr(), _stream())
+        ctx.slope, ctx.seg_rows = slope, seg_rows
+        ctx.save_for_backward(x, gamma, beta, mean, rstd, arg)
+        ctx.mark_non_differentiable(mean, var)
+        return pooled, mean, var
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gp, _gm, _gv):
+        x, gamma, beta, mean, rstd, arg = ctx.saved_tensors
+        gp = _c(gp)
+        R, C = x.shape
+        dev = x.device
+        gprime = torch.empty_like(gp)
+        sg = torch.empty((C,), device=dev, dtype=torch.float32)
+        sgx = torch.empty_like(sg)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        L().bn_pool_bwd(gp.data_ptr(), x.data_ptr(), arg.data_ptr(), R, C, ctx.seg_rows, mean.data_ptr(), rstd.data_ptr(),
+                        gamma.data_ptr(), beta.data_ptr(), ctx.slope, gprime.data_ptr(), sg.data_ptr(), sgx.data_ptr(),
+                        dx.data_ptr() if dx is not None else None, _stream())
+        return dx, sgx, sg, None, None, None
+
+
+FUSE_BN_POOL = _os.environ.get("SPGAN_FUSE_BN_POOL", "1") != "0"
+
+
+def batch_norm_act_segmax(y, bn, slope, seg_rows):
+    """max over each cloud of LeakyReLU(BatchNorm(y)): the fused kernel on the first-order train-mode path,
+    the generic chain (batch_norm_act + SegMax) in eval mode and under the gradient penalty's double backward."""
+    R, C = y.shape
+    if (FUSE_BN_POOL and bn.training and bn.track_running_stats and not _TWICE_DIFFERENTIABLE and C % 4 == 0
+            and 0.0 < slope <= 1.0):
+        pooled, mean, var = BatchNormActSegMaxTrain.apply(y, bn.weight, bn.bias, bn.eps, slope, seg_rows)
+        bn_update_running(mean, var, R, bn)
+        return pooled
+    return SegMax.apply(batch_norm_act(y, bn, slope), seg_rows)
+
+
 class NormAffineEval(Function):
     """Eval-mode BN (+activation): y = act((x - rm) * rstd * gamma + beta) with frozen statistics."""
 
@@ -789,6 +846,123 @@ class SoftmaxMulK(Function):
                               dx.data_ptr() if dx is not None else None, dy.data_ptr() if dy is not None else None,
                               _stream())
         return dx, dy, None
+
+
+class RowSoftmax(Function):
+    """softmax over the last axis of [R, N] (the attention map of --attn, modules.py:552). First-order only."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(_rows2d(x))
+        R, N = x.shape
+        y = torch.empty_like(x)
+        L().row_softmax(x.data_ptr(), R, N, y.data_ptr(), _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _c(g)
+        R, N = y.shape
+        dx = torch.empty_like(y)
+        L().row_softmax_bwd(g.data_ptr(), y.data_ptr(), R, N, dx.data_ptr(), _stream())
+        return dx
+
+
+class SegGemm(Function):
+    """Per-cloud product (torch.bmm over row blocks): A [nseg*ra, ca], B [nseg*rb, cb] -> C [nseg*M, N] with
+    C_s = A_s op(B_s), op = transpose when tb.  One spgan_gemm launch per cloud.  First-order only
+    (used by the optional Attention block, modules.py:552-554)."""
+
+    @staticmethod
+    def forward(ctx, A, B, nseg, tb):
+        A, B = _c(_rows2d(A)), _c(_rows2d(B))
+        ra, rb = A.shape[0] // nseg, B.shape[0] // nseg
+        M, N = ra, (rb if tb else B.shape[1])
+        out = torch.empty((nseg * M, N), device=A.device, dtype=torch.float32)
+        for s in range(nseg):
+            gemm_raw(A[s * ra:(s + 1) * ra], B[s * rb:(s + 1) * rb], None, False, tb, out=out[s * M:(s + 1) * M])
+        ctx.dims = (nseg, tb, ra, rb)
+        ctx.save_for_backward(A, B)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        A, B = ctx.saved_tensors
+        nseg, tb, ra, rb = ctx.dims
+        g = _c(g)
+        M = ra
+        dA = torch.empty_like(A) if ctx.needs_input_grad[0] else None
+        dB = torch.empty_like(B) if ctx.needs_input_grad[1] else None
+        for s in range(nseg):
+            As, Bs, gs = A[s * ra:(s + 1) * ra], B[s * rb:(s + 1) * rb], g[s * M:(s + 1) * M]
+            if dA is not None:      # C = A op(B): dA = g op(B)^T
+                gemm_raw(gs, Bs, None, False, not tb, out=dA[s * ra:(s + 1) * ra])
+            if dB is not None:      # tb: C = A B^T -> dB = g^T A;  else C = A B -> dB = A^T g
+                if tb:
+                    gemm_raw(gs, As, None, True, False, out=dB[s * rb:(s + 1) * rb])
+                else:
+                    gemm_raw(As, gs, None, True, False, out=dB[s * rb:(s + 1) * rb])
+        return dA, dB, None, None
+
+
+class BnActSoftmaxMulKTrain(Function):
+    """prod = lrelu(bn_y(xy)) * softmax_k(lrelu(bn_w(xw))) with both train-mode BatchNorm2d + LeakyReLU
+    applications folded into the loads (EdgeBlock, Generator.py:78-82): the two normalised [E, C] tensors are
+    never written (4 fewer full-tensor passes per EdgeBlock forward).  xw, xy are the PRE-normalisation
+    tensors [P*k, C].  Returns (prod, mean_w, var_w, mean_y, var_y).  First-order only."""
+
+    @staticmethod
+    def forward(ctx, xw, gamma_w, beta_w, xy, gamma_y, beta_y, eps_w, eps_y, slope, k):
+        xw, xy = _c(_rows2d(xw)), _c(_rows2d(xy))
+        E, C = xw.shape
+        mean_w, rstd_w, var_w = col_stats(xw, E, eps_w)
+        mean_y, rstd_y, var_y = col_stats(xy, E, eps_y)
+        w = torch.empty_like(xw)
+        prod = torch.empty_like(xw)
+        L().bn_softmax_mul_k(xw.data_ptr(), xy.data_ptr(), E // k, k, C, mean_w.data_ptr(), rstd_w.data_ptr(),
+                             gamma_w.data_ptr(), beta_w.data_ptr(), mean_y.data_ptr(), rstd_y.data_ptr(),
+                             gamma_y.data_ptr(), beta_y.data_ptr(), slope, w.data_ptr(), prod.data_ptr(), _stream())
+        ctx.k, ctx.slope = k, slope
+        ctx.save_for_backward(xw, xy, w, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y)
+        ctx.mark_non_differentiable(mean_w, var_w, mean_y, var_y)
+        return prod, mean_w, var_w, mean_y, var_y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, *_unused):
+        xw, xy, w, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y = ctx.saved_tensors
+        g = _c(g)
+        E, C = xw.shape
+        dwa = torch.empty_like(xw)
+        dya = torch.empty_like(xw)
+        L().bn_softmax_mul_k_bwd(g.data_ptr(), xy.data_ptr(), w.data_ptr(), E // ctx.k, ctx.k, C, mean_y.data_ptr(),
+                                 rstd_y.data_ptr(), gamma_y.data_ptr(), beta_y.data_ptr(), ctx.slope, dwa.data_ptr(),
+                                 dya.data_ptr(), _stream())
+        dxw, sg_w, sgx_w = _norm_bwd(dwa, xw, ctx.slope, E, mean_w, rstd_w, gamma_w, beta_w)
+        del dwa
+        dxy, sg_y, sgx_y = _norm_bwd(dya, xy, ctx.slope, E, mean_y, rstd_y, gamma_y, beta_y)
+        return dxw, sgx_w.view(-1), sg_w.view(-1), dxy, sgx_y.view(-1), sg_y.view(-1), None, None, None, None
+
+
+FUSE_EDGE_ATTENTION = _os.environ.get("SPGAN_FUSE_EDGE_ATTENTION", "1") != "0"
+
+
+def bn_act_softmax_mul_k(xw, bn_w, xy, bn_y, slope, k):
+    """EdgeBlock's y * softmax_k(w) over the two BatchNorm2d + LeakyReLU branches (Generator.py:78-82), fused on
+    the train-mode path; eval mode runs the generic chain."""
+    E = xw.shape[0]
+    if (FUSE_EDGE_ATTENTION and k <= 16 and bn_w.training and bn_y.training and bn_w.track_running_stats
+            and bn_y.track_running_stats and not _TWICE_DIFFERENTIABLE):
+        prod, mean_w, var_w, mean_y, var_y = BnActSoftmaxMulKTrain.apply(
+            xw, bn_w.weight, bn_w.bias, xy, bn_y.weight, bn_y.bias, bn_w.eps, bn_y.eps, slope, k)
+        bn_update_running(mean_w, var_w, E, bn_w)
+        bn_update_running(mean_y, var_y, E, bn_y)
+        return prod
+    return SoftmaxMulK.apply(batch_norm_act(xw, bn_w, slope), batch_norm_act(xy, bn_y, slope), k)
 
 
 class KMax(Function):

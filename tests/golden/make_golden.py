@@ -41,7 +41,13 @@ def pack(t):
     return a
 
 
+ONLY = [t for t in os.environ.get("SPGAN_GOLDEN_ONLY", "").split(",") if t]     # e.g. generator_eql_attn
+
+
 def save(name, **arrays):
+    if ONLY and name not in ONLY:
+        print("skipped %s (SPGAN_GOLDEN_ONLY)" % name)
+        return
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **arrays)
     print("wrote %-28s %8.1f KB  keys=%d" % (name + ".npz", os.path.getsize(path) / 1024, len(arrays)))
@@ -272,7 +278,8 @@ def main():
 
     # ------------------------------------------------------------------ Generator
     ball256 = sphere(256).astype(np.float32)
-    for tag, kw in (("default", {}), ("off_znorm", {"off": True, "z_norm": True}), ("use_head", {"use_head": True})):
+    for tag, kw in (("default", {}), ("off_znorm", {"off": True, "z_norm": True}), ("use_head", {"use_head": True}),
+                    ("eql_attn", {"eql": True, "attn": True})):
         o = R.default_opts(np=256, **kw)
         rng = np.random.default_rng(50)
         Bg = 4
@@ -292,6 +299,11 @@ def main():
         _, idx1 = get_edge_features(xg.transpose(2, 1).contiguous(), o.nk // 2, return_idx=True)
         arrs = {"z": zg.numpy()[:, :1].copy(), "r": rg.numpy(), "out_train": out.detach().numpy(),
                 "x1": feats["x1"].numpy(), "edgeconv2_out": pack(feats["e2"])}
+        if tag == "eql_attn":
+            # non-default flags: forward + parameter gradients, EdgeConv2's list for injection
+            _, idx2 = get_edge_features(feats["x1"], o.nk // 2, return_idx=True)
+            arrs["idx2"] = idx2.view(Bg, 256, -1).numpy().astype(np.int16)
+            arrs.update(grads_of(G))
         if tag == "default":
             _, idx2 = get_edge_features(feats["x1"], o.nk // 2, return_idx=True)
             arrs["idx1"] = idx1.view(Bg, 256, -1).numpy().astype(np.int16)

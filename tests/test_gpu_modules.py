@@ -139,7 +139,7 @@ def test_gradient_penalty_double_backward():
 
 
 @pytest.mark.parametrize("tag,kw", [("default", {}), ("off_znorm", {"off": True, "z_norm": True}),
-                                    ("use_head", {"use_head": True})])
+                                    ("use_head", {"use_head": True}), ("eql_attn", {"eql": True, "attn": True})])
 def test_generator(tag, kw, sphere256):
     pkg = _pkg()
     g = golden("generator_" + tag)
@@ -149,6 +149,8 @@ def test_generator(tag, kw, sphere256):
     Bg = g["out_train"].shape[0]
     x = torch.from_numpy(np.tile(sphere256[None], (Bg, 1, 1))).cuda()
     z = torch.from_numpy(np.tile(g["z"], (1, 256, 1))).cuda()
+    if tag == "eql_attn":
+        G.debug_idx = (None, torch.from_numpy(g["idx2"].astype(np.int32)).cuda())
     if tag == "default":
         # kNN indices through the generator must be bit-exact where the input features are: EdgeConv1
         # sees the sphere itself; for EdgeConv2 inject the reference's own list so that feature parity is
@@ -161,6 +163,12 @@ def test_generator(tag, kw, sphere256):
         assert np.array_equal(idx1, g["idx1"].astype(np.int32))
         assert_rel(G._last_x1.view(Bg, 256, 64).permute(0, 2, 1), g["x1"], TOL, "x1")
     assert_rel(out, g["out_train"], TOL, "out_train")
+    if tag == "eql_attn":
+        # non-default flags: same state_dict keys (head.N.conv.weight_orig, attn.*), forward and
+        # parameter gradients against the reference; max_tol as for the default generator (mask flips)
+        assert "head.0.conv.weight_orig" in G.state_dict() and "attn.gamma" in G.state_dict()
+        _scalar_loss(out, torch.from_numpy(g["r"]).cuda()).backward()
+        _check_grads(G, g, tol=5e-3)
     if tag != "default":
         return
     _scalar_loss(out, torch.from_numpy(g["r"]).cuda()).backward()

@@ -409,3 +409,104 @@ def test_adam_matches_torch():
         gg = g.cuda()
         ops.L().adam_step(p.data_ptr(), gg.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-4, 0.5, 0.99, 1e-8, t, 1.0, None)
     close(p, pr.detach(), 1e-6)
+
+
+# ------------------------------------------------------------------------------- fused BN + LeakyReLU + max pool
+@pytest.mark.parametrize("B,N,C", [(3, 50, 64), (2, 2048, 1024), (5, 333, 132)])
+def test_bn_act_segmax_fused_matches_torch(B, N, C):
+    """Discriminator.py:77-81,104: BatchNorm1d(train) -> LeakyReLU -> max over points, against torch CPU
+    (values, arg-max routing of the gradient, BN parameter gradients); gamma has both signs and a zero."""
+    ops = _ops()
+    slope, eps = 0.01, 1e-5
+    x = rnd(B * N, C, seed=11)
+    gamma = rnd(C, seed=12)
+    gamma[3] = 0.0
+    beta = rnd(C, seed=13)
+    gout = rnd(B, C, seed=14)
+    xr = x.clone().double().requires_grad_()
+    gr, br = gamma.clone().double().requires_grad_(), beta.clone().double().requires_grad_()
+    y = F.leaky_relu(F.batch_norm(xr, None, None, gr, br, True, 0.0, eps), slope)
+    ref = y.view(B, N, C).max(dim=1).values
+    ref.backward(gout.double())
+
+    xg = x.cuda().requires_grad_()
+    gg, bg = gamma.cuda().requires_grad_(), beta.cuda().requires_grad_()
+    pooled, mean, var = ops.BatchNormActSegMaxTrain.apply(xg, gg, bg, eps, slope, N)
+    pooled.backward(gout.cuda())
+    close(pooled, ref.float(), TIGHT, "pooled")
+    close(mean.view(-1), x.double().mean(0).float(), TIGHT, "mean")
+    close(var.view(-1), x.double().var(0, unbiased=False).float(), TIGHT, "var")
+    close(gg.grad, gr.grad.float(), 1e-4, "dgamma")
+    close(bg.grad, br.grad.float(), 1e-4, "dbeta")
+    close(xg.grad, xr.grad.float(), 1e-4, "dx")
+
+
+def test_bn_act_segmax_module_path_matches_unfused():
+    """batch_norm_act_segmax (fused) == SegMax(batch_norm_act(.)) incl. the running-stat side effects."""
+    import torch.nn as nn
+    ops = _ops()
+    B, N, C = 4, 256, 128
+    x = rnd(B * N, C, seed=21)
+    outs = []
+    for fused in (True, False):
+        bn = nn.BatchNorm1d(C).cuda().train()
+        with torch.no_grad():
+            bn.weight.copy_(rnd(C, seed=22).cuda())
+            bn.bias.copy_(rnd(C, seed=23).cuda())
+        xg = x.cuda().requires_grad_()
+        prev = ops.FUSE_BN_POOL
+        ops.FUSE_BN_POOL = fused
+        try:
+            p = ops.batch_norm_act_segmax(xg, bn, 0.01, N)
+        finally:
+            ops.FUSE_BN_POOL = prev
+        p.backward(rnd(B, C, seed=24).cuda())
+        outs.append((p.detach(), xg.grad, bn.weight.grad, bn.bias.grad, bn.running_mean.clone(), bn.running_var.clone(),
+                     int(bn.num_batches_tracked)))
+    for a, b, what in zip(outs[0][:6], outs[1][:6], ["pooled", "dx", "dgamma", "dbeta", "running_mean", "running_var"]):
+        close(a, b, 1e-5, what)
+    assert outs[0][6] == outs[1][6] == 1
+
+
+# ------------------------------------------------------------------------------- fused EdgeBlock attention
+@pytest.mark.parametrize("P,k,C", [(300, 10, 128), (64, 8, 64), (50, 16, 12)])
+def test_bn_act_softmax_mul_k_fused_equals_unfused_chain(P, k, C):
+    """Generator.py:78-82 with both BatchNorm2d(train) + LeakyReLU folded into the loads: bit-identical forward,
+    gradients and running statistics equal to the generic chain; and the chain itself against torch CPU."""
+    import torch.nn as nn
+    ops = _ops()
+    xw, xy, gout = rnd(P * k, C, seed=31), rnd(P * k, C, seed=32, scale=2.0), rnd(P * k, C, seed=33)
+    res = []
+    for fused in (True, False):
+        bns = []
+        for sd in (34, 35):
+            bn = nn.BatchNorm2d(C).cuda().train()
+            with torch.no_grad():
+                bn.weight.copy_(rnd(C, seed=sd).cuda())
+                bn.bias.copy_(rnd(C, seed=sd + 10).cuda())
+            bns.append(bn)
+        a, b = xw.cuda().requires_grad_(), xy.cuda().requires_grad_()
+        prev = ops.FUSE_EDGE_ATTENTION
+        ops.FUSE_EDGE_ATTENTION = fused
+        try:
+            out = ops.bn_act_softmax_mul_k(a, bns[0], b, bns[1], 0.01, k)
+        finally:
+            ops.FUSE_EDGE_ATTENTION = prev
+        out.backward(gout.cuda())
+        res.append(dict(out=out.detach(), dxw=a.grad, dxy=b.grad, gw=bns[0].weight.grad, bw=bns[0].bias.grad,
+                        gy=bns[1].weight.grad, by=bns[1].bias.grad, rm=bns[0].running_mean.clone(),
+                        rv=bns[1].running_var.clone()))
+    assert torch.equal(res[0]["out"], res[1]["out"])
+    for key in res[0]:
+        close(res[0][key], res[1][key], 1e-5, key)
+    # torch CPU reference of the whole expression
+    a, b = xw.double().requires_grad_(), xy.double().requires_grad_()
+    g1, b1 = rnd(C, seed=34).double(), rnd(C, seed=44).double()
+    g2, b2 = rnd(C, seed=35).double(), rnd(C, seed=45).double()
+    wa = F.leaky_relu(F.batch_norm(a, None, None, g1, b1, True, 0.0, 1e-5), 0.01)
+    ya = F.leaky_relu(F.batch_norm(b, None, None, g2, b2, True, 0.0, 1e-5), 0.01)
+    ref = ya * F.softmax(wa.view(P, k, C), dim=1).view(P * k, C)
+    ref.backward(gout.double())
+    close(res[0]["out"], ref.float(), 1e-5, "out vs torch")
+    close(res[0]["dxw"], a.grad.float(), 1e-4, "dxw vs torch")
+    close(res[0]["dxy"], b.grad.float(), 1e-4, "dxy vs torch")

@@ -103,7 +103,7 @@ def test_gradient_penalty():
 
 
 @pytest.mark.parametrize("tag,kw", [("default", {}), ("off_znorm", {"off": True, "z_norm": True}),
-                                    ("use_head", {"use_head": True})])
+                                    ("use_head", {"use_head": True}), ("eql_attn", {"eql": True, "attn": True})])
 def test_generator(tag, kw, sphere256):
     g = golden("generator_" + tag)
     o = R.default_opts(np=256, **kw)
@@ -113,6 +113,9 @@ def test_generator(tag, kw, sphere256):
     out, x1 = R.generator_forward(sd, x, z, o, training=True, return_x1=True)
     assert_rel(out, g["out_train"], 1e-4, "out_train")
     assert_rel(x1, g["x1"], 1e-4, "x1")
+    if tag == "eql_attn":                  # non-default flags: equalised-lr weights + the N x N attention block
+        (out * torch.from_numpy(g["r"])).sum().backward()
+        _check_grads(sd, g, tol=5e-4)
     if tag != "default":
         return
     (out * torch.from_numpy(g["r"])).sum().backward()
