@@ -261,12 +261,28 @@ int spgan_gp_penalty_bwd(const float *g, const float *norms, const float *gout, 
 /* out[0] = scale * mean(x[0:n]) (+ out[0] if accumulate): the wgan loss means, loss_utils.py:728-730,859-863 */
 int spgan_mean(const float *x, int64_t n, float scale, int accumulate, float *out, spgan_stream_t stream);
 
+/* ------------------------------------------------------------------ evaluation: pairwise Chamfer distance
+ * cd[i*R + j - pair0] = mean_n min_m |a_i[n] - b_j[m]|^2 + mean_m min_n |a_i[n] - b_j[m]|^2 for the cloud pairs
+ * pair0 <= i*R + j < pair0 + npairs of a [S, N, 3] x b [R, M, 3] (contiguous xyz): the CD half of
+ * metrics/evaluation_metrics.py:89-125 (_pairwise_EMD_CD_) / Common/GAN_metrics.py:658-684 (pairwise_CD), with the
+ * direct-difference arithmetic of metrics/CD_EMD/cd/chamferdist/chamfer.cu:12-134.  dl / dr (the two directed
+ * means, distChamfer evaluation_metrics.py:37-49) are optional; any of cd, dl, dr may be NULL but not all.
+ * The pair range lets ranks shard the S x R matrix (BASELINE configs[4]).  N, M <= ~7000 (shared-memory staging). */
+int spgan_pairwise_chamfer(const float *a, const float *b, int S, int R, int N, int M, int64_t pair0, int64_t npairs,
+                           float *cd, float *dl, float *dr, spgan_stream_t stream);
+
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam semantics (model.py:94-97) over one flat parameter buffer: in-place update of
  * p, m, v from grad_scale * g; step is the 1-based step count.  grad_scale = 1/world_size turns the
  * summed all-reduce result into the data-parallel mean without a separate pass. */
 int spgan_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
                     float eps, int step, float grad_scale, spgan_stream_t stream);
+
+/* The same update with the step count kept on the device: state = {int32 step, float, float, pad} (16 bytes, zeroed
+ * by the caller once); every call increments state[0] first and derives the bias corrections from it.  No argument
+ * changes between steps, so a captured CUDA graph of the whole training step can be replayed. */
+int spgan_adam_step_dev(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, int32_t *state, float grad_scale, spgan_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -9,8 +9,9 @@ from .edge import get_edge_features, edgeConv, EdgeBlock  # noqa: F401
 from .generator import Generator, AdaptivePointNorm  # noqa: F401
 from .discriminator import Discriminator  # noqa: F401
 from .gradient_penalty import GradientPenalty  # noqa: F401
+from .metrics import pairwise_CD, lgan_mmd_cov, one_nn_accuracy  # noqa: F401
 from .train_step import WGANGPTrainer, dis_loss_wgan, gen_loss_wgan, requires_grad  # noqa: F401
 
 __all__ = ["ops", "get_edge_features", "edgeConv", "EdgeBlock", "Generator", "AdaptivePointNorm",
            "Discriminator", "GradientPenalty", "WGANGPTrainer", "dis_loss_wgan", "gen_loss_wgan",
-           "requires_grad"]
+           "requires_grad", "pairwise_CD", "lgan_mmd_cov", "one_nn_accuracy"]

@@ -49,7 +49,8 @@ class SpganError(RuntimeError):
 
 # kernel launches behind one C-ABI call (1 unless listed)
 _LAUNCHES = {"spgan_colsum": 2, "spgan_coldot": 2, "spgan_colstats": 2, "spgan_norm_bwd_reduce": 2,
-             "spgan_bn_dbl_bwd_reduce": 2, "spgan_bn_dbl_bwd_apply": 2, "spgan_gp_penalty": 2}
+             "spgan_bn_dbl_bwd_reduce": 2, "spgan_bn_dbl_bwd_apply": 2, "spgan_gp_penalty": 2,
+             "spgan_bn_pool_fwd": 2, "spgan_bn_pool_bwd": 2, "spgan_adam_step_dev": 2}
 
 
 class _Library:

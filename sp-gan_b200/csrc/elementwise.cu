@@ -287,6 +287,29 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Device-resident step counter variant (CUDA-graph replay: nothing that changes between steps may be a kernel
+// argument).  state = {int32 step, float 1 - beta1^step, float sqrt(1 - beta2^step), pad}.
+__global__ void adam_prep_kernel(int32_t* state, float b1, float b2) {
+    const int step = state[0] + 1;
+    state[0] = step;
+    float* f = reinterpret_cast<float*>(state);
+    f[1] = 1.f - powf(b1, (float)step);
+    f[2] = sqrtf(1.f - powf(b2, (float)step));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                const int32_t* __restrict__ state, float gscale) {
+    const float bc1 = reinterpret_cast<const float*>(state)[1], bc2_sqrt = reinterpret_cast<const float*>(state)[2];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - (lr / bc1) * (mi / denom);
+    }
+}
+
 }  // namespace
 
 extern "C" int spgan_fill(float* x, int64_t n, float v, spgan_stream_t s) {
@@ -408,6 +431,15 @@ extern "C" int spgan_adam_step(float* p, const float* g, float* m, float* v, int
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2 = 1.f - powf(beta2, (float)step);
     adam_kernel<<<ew_grid(n, 256), 256, 0, as_stream(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+    return spgan_launch_status();
+}
+
+extern "C" int spgan_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                   float beta2, float eps, int32_t* state, float grad_scale, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(p && g && m && v && state && n >= 0);
+    adam_prep_kernel<<<1, 1, 0, as_stream(s)>>>(state, beta1, beta2);
+    if (n == 0) return spgan_launch_status();
+    adam_dev_kernel<<<ew_grid(n, 256), 256, 0, as_stream(s)>>>(p, g, m, v, n, lr, beta1, beta2, eps, state, grad_scale);
     return spgan_launch_status();
 }
 

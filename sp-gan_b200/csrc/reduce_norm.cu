@@ -563,6 +563,7 @@ struct BnCol { const float* mean; const float* rstd; const float* gamma; const f
 __device__ __forceinline__ float bn_act(float x, float m, float r, float g, float b, float slope) {
     return lrelu_f(fmaf((x - m) * r, g, b), slope);
 }
+template <int KM>
 __global__ void __launch_bounds__(256)
 bn_softmax_mul_k_kernel(const float* __restrict__ xw, const float* __restrict__ xy, int64_t P, int k, int C, BnCol bw,
                         BnCol by, float slope, float* __restrict__ w, float* __restrict__ prod) {
@@ -571,24 +572,28 @@ bn_softmax_mul_k_kernel(const float* __restrict__ xw, const float* __restrict__ 
         const int64_t p = i / C;
         const int c = (int)(i - p * C);
         const int64_t o = p * k * C + c;
+        // all 2k loads of this (point, channel) are issued before anything depends on them
+        float a[KM], b[KM];
+#pragma unroll
+        for (int r = 0; r < KM; ++r)
+            if (r < k) { a[r] = __ldg(xw + o + (int64_t)r * C); b[r] = __ldg(xy + o + (int64_t)r * C); }
         const float mw = __ldg(bw.mean + c), rw = __ldg(bw.rstd + c), gw = __ldg(bw.gamma + c), bbw = __ldg(bw.beta + c);
         const float my = __ldg(by.mean + c), ry = __ldg(by.rstd + c), gy = __ldg(by.gamma + c), bby = __ldg(by.beta + c);
-        float a[KMAXR];
         float m = -FLT_MAX;
 #pragma unroll
-        for (int r = 0; r < KMAXR; ++r)
-            if (r < k) { a[r] = bn_act(__ldg(xw + o + (int64_t)r * C), mw, rw, gw, bbw, slope); m = fmaxf(m, a[r]); }
+        for (int r = 0; r < KM; ++r)
+            if (r < k) { a[r] = bn_act(a[r], mw, rw, gw, bbw, slope); m = fmaxf(m, a[r]); }
         float s = 0.f;
 #pragma unroll
-        for (int r = 0; r < KMAXR; ++r)
+        for (int r = 0; r < KM; ++r)
             if (r < k) { a[r] = expf(a[r] - m); s += a[r]; }
         const float inv = 1.f / s;
 #pragma unroll
-        for (int r = 0; r < KMAXR; ++r)
+        for (int r = 0; r < KM; ++r)
             if (r < k) {
                 const float wr = a[r] * inv;
                 w[o + (int64_t)r * C] = wr;
-                prod[o + (int64_t)r * C] = wr * bn_act(__ldg(xy + o + (int64_t)r * C), my, ry, gy, bby, slope);
+                prod[o + (int64_t)r * C] = wr * bn_act(b[r], my, ry, gy, bby, slope);
             }
     }
 }
@@ -987,8 +992,11 @@ extern "C" int spgan_bn_softmax_mul_k(const float* xw, const float* xy, int64_t 
     SPGAN_CHECK_ARG(P >= 0 && k >= 1 && C >= 1);
     if (k > KMAXR) return SPGAN_E_UNSUPPORTED;
     if (P == 0) return SPGAN_OK;
-    bn_softmax_mul_k_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(
-        xw, xy, P, k, C, BnCol{mean_w, rstd_w, gamma_w, beta_w}, BnCol{mean_y, rstd_y, gamma_y, beta_y}, slope, w, prod);
+    const BnCol cw{mean_w, rstd_w, gamma_w, beta_w}, cy{mean_y, rstd_y, gamma_y, beta_y};
+    if (k <= 10)
+        bn_softmax_mul_k_kernel<10><<<ew_grid(P * C, 256, 32), 256, 0, as_stream(s)>>>(xw, xy, P, k, C, cw, cy, slope, w, prod);
+    else
+        bn_softmax_mul_k_kernel<KMAXR><<<ew_grid(P * C, 256, 32), 256, 0, as_stream(s)>>>(xw, xy, P, k, C, cw, cy, slope, w, prod);
     return spgan_launch_status();
 }
 extern "C" int spgan_bn_softmax_mul_k_bwd(const float* g, const float* xy, const float* w, int64_t P, int k, int C,

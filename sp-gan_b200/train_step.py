@@ -31,16 +31,33 @@ def gen_loss_wgan(d_fake):
     return ops.MeanScale.apply(d_fake, -1.0)
 
 
+def _dense_copy_(dst, src):
+    """dst.copy_(src) as ONE memcpy when both are the same permutation of a dense tensor (e.g. the transposed
+    [B,3,N] view of a [B,N,3] batch, model.py:249): keeps pinned-host -> device copies asynchronous."""
+    order = sorted(range(dst.dim()), key=lambda i: -dst.stride(i))
+    d, s_ = dst.permute(order), src.permute(order)
+    if d.is_contiguous() and s_.is_contiguous():
+        d.copy_(s_, non_blocking=True)
+    else:
+        dst.copy_(src, non_blocking=True)
+
+
 class FlatAdam:
     """torch.optim.Adam semantics (model.py:94-97) as ONE fused kernel over the flat parameter buffer,
-    preceded by ONE all-reduce of the flat gradient buffer when running data parallel."""
+    preceded by ONE all-reduce of the flat gradient buffer when running data parallel.  The step count lives
+    on the device (spgan_adam_step_dev), so a captured CUDA graph of the step can be replayed."""
 
     def __init__(self, module, lr=1e-4, betas=(0.5, 0.99), eps=1e-8):
         self.buf = FlatBuffers(module)
         n, dev = self.buf.numel, self.buf.flat_p.device
         self.m = ops.full((n,), 0.0, dev)
         self.v = ops.full((n,), 0.0, dev)
-        self.lr, self.betas, self.eps, self.t, self.n = lr, betas, eps, 0, n
+        self.state = torch.zeros(4, device=dev, dtype=torch.int32)      # {step, bias corrections}: see the header
+        self.lr, self.betas, self.eps, self.n = lr, betas, eps, n
+
+    @property
+    def t(self):
+        return int(self.state[0])          # host read-back (synchronises): diagnostics only
 
     def zero_grad(self):
         ops.fill_(self.buf.flat_g, 0.0)
@@ -48,10 +65,9 @@ class FlatAdam:
 
     def step(self):
         scale = self.buf.allreduce_grads()
-        self.t += 1
-        ops.L().adam_step(self.buf.flat_p.data_ptr(), self.buf.flat_g.data_ptr(), self.m.data_ptr(),
-                          self.v.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps, self.t,
-                          scale, ops._stream())
+        ops.L().adam_step_dev(self.buf.flat_p.data_ptr(), self.buf.flat_g.data_ptr(), self.m.data_ptr(),
+                              self.v.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
+                              self.state.data_ptr(), scale, ops._stream())
 
 
 class WGANGPTrainer:
@@ -64,6 +80,7 @@ class WGANGPTrainer:
         self.opt_d = FlatAdam(D, lr_d, betas)
         self.opt_g.buf.broadcast_params()
         self.opt_d.buf.broadcast_params()
+        self._graph, self._graph_out, self._static, self.graph_launches = None, None, None, 0
 
     def d_phase(self, x, z, real, alpha=None):
         G, D = self.G, self.D
@@ -98,3 +115,44 @@ class WGANGPTrainer:
         loss_d, gp = self.d_phase(x, z_d, real, alpha)
         loss_g = self.g_phase(x, z_g, real)
         return loss_d, gp, loss_g
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def capture(self, x, z_d, z_g, real, alpha, warmup=2):
+        """Record one full step (both phases, the gradient all-reduces and the Adam updates: ~700 kernel
+        launches) into a CUDA graph over static input buffers.  `warmup` eager steps run first on the capture
+        stream (they DO train, like any other step).  Afterwards `replay(...)` costs one graph launch of host
+        time per step.  All arguments must be CUDA tensors; their shapes / strides become part of the graph."""
+        if self._graph is not None:
+            raise RuntimeError("a step graph has already been captured")
+        self._static = {"x": x, "z_d": z_d.clone(memory_format=torch.preserve_format) if z_d.stride(1) else z_d[:, :1].clone().expand_as(z_d),
+                        "z_g": z_g.clone(memory_format=torch.preserve_format) if z_g.stride(1) else z_g[:, :1].clone().expand_as(z_g),
+                        "real": real.clone(memory_format=torch.preserve_format), "alpha": alpha.detach().clone()}
+        st = self._static
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(st["x"], st["z_d"], st["z_g"], st["real"], st["alpha"])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        l0 = ops.L().launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.step(st["x"], st["z_d"], st["z_g"], st["real"], st["alpha"])
+        self.graph_launches = ops.L().launches - l0          # kernels recorded in the graph
+        self._graph, self._graph_out = g, out
+        return self
+
+    def replay(self, z_d=None, z_g=None, real=None, alpha=None):
+        """Copy the new inputs into the static buffers (any of them may be omitted = unchanged) and replay the
+        captured step.  Returns the static (loss_d, gp, loss_g) device scalars, overwritten by the next replay."""
+        st = self._static
+        for key, val in (("z_d", z_d), ("z_g", z_g), ("real", real), ("alpha", alpha)):
+            if val is not None:
+                dst = st[key]
+                if dst.dim() == 3 and dst.stride(1) == 0:                 # broadcast latent: one vector per cloud
+                    dst[:, :1].copy_(val[:, :1], non_blocking=True)
+                else:
+                    _dense_copy_(dst, val)
+        self._graph.replay()
+        return self._graph_out

@@ -1,0 +1,65 @@
+"""GPU parity of spgan_pairwise_chamfer (through the C ABI) against the CPU oracle and the reference golden."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_rel, golden
+from oracle import chamfer_ref as C
+from oracle import spgan_ref as R
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3          # BASELINE.json: features/losses within 1e-3 relative (fp32)
+
+
+def _pkg():
+    import spgan_b200
+    return spgan_b200
+
+
+def test_pairwise_cd_against_reference_golden():
+    pkg = _pkg()
+    g = golden("chamfer")
+    smp, ref = torch.from_numpy(g["sample"]).cuda(), torch.from_numpy(g["ref"]).cuda()
+    cd = pkg.pairwise_CD(smp, ref)
+    assert tuple(cd.shape) == g["cd_sr"].shape
+    assert_rel(cd, g["cd_sr"], TOL, "cd_sr vs reference (expanded-form fp32)")
+    assert_rel(cd, C.pairwise_cd_exact(g["sample"], g["ref"]), 2e-5, "cd_sr vs float64 direct form")
+    ss, rr = pkg.pairwise_CD(smp, smp), pkg.pairwise_CD(ref, ref)
+    mc = pkg.lgan_mmd_cov(cd)
+    assert abs(mc["lgan_mmd"] - float(g["lgan_mmd"])) <= TOL * float(g["lgan_mmd"])
+    assert mc["lgan_cov"] == pytest.approx(float(g["lgan_cov"]))
+    assert pkg.one_nn_accuracy(ss, cd, rr) == pytest.approx(float(g["one_nn_acc"]))
+
+
+@pytest.mark.parametrize("S,Rn,N,M", [(3, 4, 100, 77), (1, 1, 1, 1), (2, 3, 129, 300), (5, 2, 2048, 2048)])
+def test_pairwise_cd_ragged_shapes_and_properties(S, Rn, N, M):
+    pkg = _pkg()
+    rng = np.random.default_rng(S * 1000 + N)
+    a = rng.standard_normal((S, N, 3)).astype(np.float32)
+    b = (0.7 * rng.standard_normal((Rn, M, 3)) + 0.1).astype(np.float32)
+    ag, bg = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    cd = pkg.pairwise_CD(ag, bg)
+    if N * M <= 300 * 300:
+        assert_rel(cd, C.pairwise_cd_exact(a, b), 2e-5, "ragged")
+    # properties that hold at any size: symmetry under swapping the sets, zero self distance, shard == whole
+    assert_rel(pkg.pairwise_CD(bg, ag), cd.t().contiguous().cpu().numpy(), 1e-6, "symmetry (summation order differs)")
+    self_cd = pkg.pairwise_CD(ag, ag)
+    assert float(self_cd.diagonal().abs().max()) == 0.0
+    ops = pkg.ops
+    part = torch.empty(S * Rn, device="cuda")
+    half = (S * Rn) // 2
+    for p0, n in ((0, half), (half, S * Rn - half)):
+        if n:
+            ops.L().pairwise_chamfer(ag.data_ptr(), bg.data_ptr(), S, Rn, N, M, p0, n, part[p0:].data_ptr(), None, None,
+                                     ops._stream())
+    assert torch.equal(part.view(S, Rn), cd)
+
+
+def test_pairwise_cd_on_synthetic_chairs_full_size():
+    """BASELINE configs[4] shape per pair (N = 2048) on a few clouds, against the float64 oracle."""
+    pkg = _pkg()
+    rng = np.random.default_rng(5)
+    a = R.synthetic_chairs(rng, 3, 2048)
+    b = R.synthetic_chairs(rng, 2, 2048)
+    cd = pkg.pairwise_CD(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert_rel(cd, C.pairwise_cd_exact(a, b), 2e-5, "chairs 2048")

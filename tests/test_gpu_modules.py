@@ -267,3 +267,48 @@ def test_modules_fail_loudly_on_cpu_tensors():
     D = pkg.Discriminator(R.default_opts())
     with pytest.raises(RuntimeError, match="CUDA"):
         D(torch.zeros(2, 3, 64))
+
+
+def test_train_step_graph_replay_equals_eager(sphere256):
+    """WGANGPTrainer.capture/replay (one CUDA graph per step) against the eager trainer: same kernels, same
+    inputs => the same losses and parameters after every step, and the Adam step count advances on the device."""
+    pkg = _pkg()
+    o = R.default_opts(np=256)
+    B, N = 2, 256
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(np.tile(sphere256[None], (B, 1, 1))).cuda()
+    batches = [dict(z_d=torch.from_numpy(R.latent_noise(rng, B, N, o.nz)[:, :1].copy()).cuda(),
+                    z_g=torch.from_numpy(R.latent_noise(rng, B, N, o.nz)[:, :1].copy()).cuda(),
+                    real=torch.from_numpy(R.synthetic_chairs(rng, B, N)).cuda(),
+                    alpha=torch.rand(B, 1, 1, generator=torch.Generator().manual_seed(i)).cuda()) for i in range(4)]
+    runs = []
+    for graph in (False, True):
+        G = _load(pkg.Generator(o), R.generator_spec(o), 61).train()
+        D = _load(pkg.Discriminator(o), R.discriminator_spec(o), 62).train()
+        tr = pkg.WGANGPTrainer(G, D)
+        call = lambda d: tr.step(x, d["z_d"].expand(B, N, o.nz), d["z_g"].expand(B, N, o.nz), d["real"].transpose(2, 1),
+                                 alpha=d["alpha"])
+        out = []
+        if graph:
+            d = batches[0]
+            tr.capture(x, d["z_d"].expand(B, N, o.nz), d["z_g"].expand(B, N, o.nz), d["real"].transpose(2, 1), d["alpha"],
+                       warmup=0)
+            assert tr.graph_launches > 100
+            for d in batches:
+                res = tr.replay(z_d=d["z_d"], z_g=d["z_g"], real=d["real"].transpose(2, 1), alpha=d["alpha"])
+                out.append([float(t) for t in res])
+        else:
+            for d in batches:
+                out.append([float(t) for t in call(d)])
+        runs.append((out, tr.opt_d.t, tr.opt_g.t, tr.opt_d.buf.flat_p.clone(), tr.opt_g.buf.flat_p.clone()))
+    (eo, edt, egt, edp, egp), (go, gdt, ggt, gdp, ggp) = runs
+    assert edt == gdt == 4 and egt == ggt == 4
+    # fp32 atomics in the weight-gradient kernels make runs differ at rounding level; Adam's first steps turn any
+    # difference into +-lr per element, so parameters agree to a few lr and losses to the usual tolerance
+    # (the first step starts from identical weights: tight; later ones inherit the chaotic divergence documented in
+    # DESIGN.md "Parity" -- the reference itself is only reproducible to ~10 % there)
+    for step, (a, b) in enumerate(zip(eo, go)):
+        tol = 1e-3 if step == 0 else 0.3
+        for va, vb in zip(a, b):
+            assert abs(va - vb) <= tol * max(1.0, abs(va)), (step, eo, go)
+    assert float((edp - gdp).abs().max()) <= 1e-3 and float((egp - ggp).abs().max()) <= 1e-3
