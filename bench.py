@@ -109,7 +109,7 @@ def cpu_step_time(batch, points, steps, warmup, seed=123):
     return sum(times) / len(times), torch.get_num_threads()
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -129,7 +129,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=real_stdout, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -139,10 +139,33 @@ def gemm_flops(args_):
     return 2.0 * args_[2] * args_[3] * args_[4]
 
 
+def _claim_stdout():
+    """Rank 0 must print exactly ONE line on stdout: park the real stdout and point fd 1 at stderr, so that
+    anything a library writes there (NCCL prints its version banner on stdout) cannot end up next to the JSON."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
+    real_stdout = _claim_stdout()
+    try:
+        if args.impl == "reference":
+            run_reference(args, real_stdout)
+        else:
+            run_gpu(args, real_stdout)
+    finally:
+        real_stdout.flush()
+        sys.stdout.flush()
+        sys.stderr.flush()
+    # leave without interpreter / NCCL teardown: destroying a process group whose collectives live inside a
+    # captured CUDA graph can block; every rank has passed the final barrier by now
+    os._exit(0)
+
+
+def run_gpu(args, real_stdout):
 
     import numpy as np
     import torch
@@ -399,9 +422,10 @@ def main():
                 "roofline_all_gemm": roofline_all, "roofline_knn": roofline_knn, "submetrics": sub,
                 "kernel_share": kernel_share, "cpu_baseline": cpu_baseline,
                 "last_losses": losses[-1] if losses else None}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+    torch.cuda.synchronize()
 
 
 if __name__ == "__main__":

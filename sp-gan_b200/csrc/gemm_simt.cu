@@ -294,6 +294,10 @@ bool spgan_gemm_tc_tn_supported(int64_t Mo, int No, int64_t K, const float* A, i
 int spgan_gemm_tc_tn(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                      int64_t ldc, int accumulate, void* workspace, cudaStream_t st);
 
+bool spgan_gemm_tn_skinny_supported(int64_t Mo, int No, int64_t K);
+int spgan_gemm_tn_skinny(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                         float* C, int64_t ldc, int accumulate, cudaStream_t st);
+
 extern "C" size_t spgan_gemm_workspace(int engine, int N, int K) {
     if (N < 1 || K < 1) return 0;
     // deterministic split-K partial tiles of the small-batch path (any engine)
@@ -317,6 +321,9 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
         bias == nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
         spgan_gemm_tc_tn_supported(M, N, K, A, lda, B, ldb))
         return spgan_gemm_tc_tn(M, N, K, A, lda, B, ldb, C, ldc, accumulate, workspace, as_stream(stream));
+    // tall-skinny weight gradients (tiny output, K = #points / #edges): stream K once (any engine)
+    if (transA && !transB && bias == nullptr && spgan_gemm_tn_skinny_supported(M, N, K))
+        return spgan_gemm_tn_skinny(M, N, K, A, lda, B, ldb, C, ldc, accumulate, as_stream(stream));
     return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream),
                            workspace, workspace_bytes);
 }

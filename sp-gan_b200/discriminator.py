@@ -33,9 +33,9 @@ class Discriminator(nn.Module):
         B, _, N = x.shape
         h = ops.BcnToRows.apply(x)                                               # [B*N, 3]
         for conv, bn in ((self.mlps[0], self.mlps[1]), (self.mlps[3], self.mlps[4]), (self.mlps[6], self.mlps[7])):
-            h = ops.batch_norm_act(ops.linear(h, conv.weight, conv.bias), bn, NEG)
+            h = ops.batch_norm_act(ops.linear(h, conv.weight, conv.bias, zero_bias_grad=ops.feeds_train_bn(bn)), bn, NEG)
         # fc2 -> BN -> LeakyReLU -> max over points: fused, the [B*N, dim] normalised tensor is never written
-        h = ops.linear(h, self.fc2[0].weight, self.fc2[0].bias)
+        h = ops.linear(h, self.fc2[0].weight, self.fc2[0].bias, zero_bias_grad=ops.feeds_train_bn(self.fc2[1]))
         h = ops.batch_norm_act_segmax(h, self.fc2[1], NEG, N)                    # [B, dim]
         for i in (0, 2, 4):
             h = ops.LRelu.apply(ops.linear(h, self.mlp[i].weight, self.mlp[i].bias), NEG)

@@ -71,7 +71,7 @@ class edgeConv(nn.Module, _KnnMixin):
         W = self.conv.conv.weight.view(F, 2 * C)
         a = ops.linear(x_rows, W[:, :C])                  # centre half, per point
         d = ops.linear(x_rows, W[:, C:], engine=0)        # difference half, per point (differenced: exact fp32)
-        y = ops.EdgeCombine.apply(a, d, self.conv.conv.bias, idx32, N, self.k)
+        y = ops.EdgeCombine.apply(a, d, self.conv.conv.bias, idx32, N, self.k, ops.feeds_train_bn(self.conv.bn))
         y = ops.batch_norm_act(y, self.conv.bn, 0.0)
         return ops.KMax.apply(y, self.k)
 
@@ -105,14 +105,14 @@ class EdgeBlock(nn.Module, _KnnMixin):
         cx, bx, _ = self.conv_x
         # conv_w on the difference half: W (x_j - x_i) + b == (W x)_j - (W x)_i + b
         p1 = ops.linear(x_rows, cw0.weight, engine=0)          # differenced below: exact fp32 products
-        w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k)             # [P*k, F/2]
+        w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))   # [P*k, F/2]
         w = ops.batch_norm_act(w, bw0, NEG)
-        w = ops.linear(w, cw1.weight, cw1.bias)                                  # [P*k, F], pre-BN
+        w = ops.linear(w, cw1.weight, cw1.bias, zero_bias_grad=ops.feeds_train_bn(bw1))   # [P*k, F], pre-BN
         # conv_x on [centre, difference]
         Wx = cx.weight.view(F, 2 * C)
         a = ops.linear(x_rows, Wx[:, :C])
         d = ops.linear(x_rows, Wx[:, C:], engine=0)
-        y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k)                   # [P*k, F], pre-BN
+        y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k, ops.feeds_train_bn(bx))   # [P*k, F], pre-BN
         # BN + LeakyReLU on both branches, softmax over k, then y * w: one fused pass
         y = ops.bn_act_softmax_mul_k(w, bw1, y, bx, NEG, k)
         # conv_out: kernel [1, k] == one dense contraction over (neighbour, channel)

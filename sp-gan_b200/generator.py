@@ -217,8 +217,8 @@ class Generator(nn.Module):
 
         g = ops.SegMax.apply(x2, N)                                              # [B, 128]
         gc = self.global_conv
-        g = ops.batch_norm_act(ops.linear(g, gc[0].weight, gc[0].bias), gc[1], NEG)
-        g = ops.batch_norm_act(ops.linear(g, gc[3].weight, gc[3].bias), gc[4], NEG)   # [B, 512]
+        g = ops.batch_norm_act(ops.linear(g, gc[0].weight, gc[0].bias, zero_bias_grad=ops.feeds_train_bn(gc[1])), gc[1], NEG)
+        g = ops.batch_norm_act(ops.linear(g, gc[3].weight, gc[3].bias, zero_bias_grad=ops.feeds_train_bn(gc[4])), gc[4], NEG)   # [B, 512]
 
         W0 = self.tail[0].weight.view(self.tail[0].weight.shape[0], -1)
         ng = g.shape[1]

@@ -172,10 +172,11 @@ class Gemm(Function):
     projections that EdgeCombine differences (pn[j] - pn[p]) use engine 0 (exact fp32 FMA chains)."""
 
     @staticmethod
-    def forward(ctx, A, B, bias, ta, tb, engine=None):
+    def forward(ctx, A, B, bias, ta, tb, engine=None, zero_bias_grad=False):
         ctx.ta, ctx.tb = ta, tb
         ctx.save_for_backward(A, B)
         ctx.has_bias = bias is not None
+        ctx.zero_bias_grad = zero_bias_grad
         return gemm_raw(A, B, bias, ta, tb, engine=engine)
 
     @staticmethod
@@ -190,14 +191,26 @@ class Gemm(Function):
         if ctx.needs_input_grad[1] and params_too:
             dB = Gemm.apply(A, g, None, not ta, False) if not tb else Gemm.apply(g, A, None, True, ta)
         if ctx.has_bias and ctx.needs_input_grad[2] and params_too:
-            db = ColSum.apply(g, g.shape[0]).view(-1)
-        return dA, dB, db, None, None, None
+            db = full((g.shape[1],), 0.0, g.device) if ctx.zero_bias_grad else ColSum.apply(g, g.shape[0]).view(-1)
+        return dA, dB, db, None, None, None, None
 
 
-def linear(x, weight, bias=None, engine=None):
+# A bias added right before a train-mode BatchNorm has an exactly zero gradient (the batch mean removes it; the
+# gradient reaching the conv sums to zero over the batch): the reference computes rounding noise there (~1e-7 of the
+# layer's gradient scale).  With this switch on, those gradients are returned as exact zeros instead of spending a
+# full read of the [rows, C] gradient tensor on the noise (SPGAN_EXACT_ZERO_BIAS_GRAD=0 restores the reduction).
+EXACT_ZERO_BIAS_GRAD = _os.environ.get("SPGAN_EXACT_ZERO_BIAS_GRAD", "1") != "0"
+
+
+def feeds_train_bn(bn):
+    """True when a bias added just before `bn` cannot receive gradient: train-mode batch statistics."""
+    return EXACT_ZERO_BIAS_GRAD and (bn.training or not bn.track_running_stats)
+
+
+def linear(x, weight, bias=None, engine=None, zero_bias_grad=False):
     """x [R, Cin] @ weight[Cout, Cin(,1(,1))]^T + bias -- Conv1d(k=1) / Conv2d(1x1) / Linear."""
     w = weight.reshape(weight.shape[0], -1) if weight.dim() != 2 else weight
-    return Gemm.apply(x, w, bias, False, True, engine)
+    return Gemm.apply(x, w, bias, False, True, engine, zero_bias_grad)
 
 
 # =========================================================================================
@@ -996,7 +1009,8 @@ class EdgeCombine(Function):
     expressed through per-point projections (pc may be None for a conv on the difference half)."""
 
     @staticmethod
-    def forward(ctx, pc, pn, bias, idx, N, k):
+    def forward(ctx, pc, pn, bias, idx, N, k, zero_bias_grad=False):
+        ctx.zero_bias_grad = zero_bias_grad
         pn = _c(_rows2d(pn))
         P, C = pn.shape
         if pc is not None:
@@ -1024,8 +1038,8 @@ class EdgeCombine(Function):
                              dpn.data_ptr(), _stream())
         db = None
         if has_bias and ctx.needs_input_grad[2]:
-            db = ColSum.apply(g, g.shape[0]).view(-1)
-        return dpc, dpn, db, None, None, None
+            db = full((C,), 0.0, g.device) if ctx.zero_bias_grad else ColSum.apply(g, g.shape[0]).view(-1)
+        return dpc, dpn, db, None, None, None, None
 
 
 # =========================================================================================

@@ -411,6 +411,22 @@ def test_adam_matches_torch():
     close(p, pr.detach(), 1e-6)
 
 
+@pytest.mark.parametrize("Mo,No,K", [(64, 32, 20000), (64, 3, 16500), (33, 17, 40001), (1, 1, 16384)])
+def test_gemm_tall_skinny_weight_gradient(Mo, No, K):
+    """C = A^T B with a tiny output and K = #points (EdgeConv1 conv_w.3 / first-layer weight gradients)."""
+    ops = _ops()
+    A, B = rnd(K, Mo, seed=5), rnd(K, No, seed=6)
+    ref = (A.double().t() @ B.double()).float()
+    out = ops.gemm_raw(A.cuda(), B.cuda(), None, True, False)
+    close(out, ref, 2e-5, "skinny TN")
+    out2 = ops.gemm_raw(A.cuda(), B.cuda(), None, True, False, out=out, accumulate=True)
+    close(out2, 2 * ref, 2e-5, "skinny TN accumulate")
+    # strided operands (column slices of wider row-major matrices)
+    Aw, Bw = rnd(K, Mo + 5, seed=7).cuda(), rnd(K, No + 3, seed=8).cuda()
+    out3 = ops.gemm_raw(Aw[:, 2:2 + Mo], Bw[:, 1:1 + No], None, True, False)
+    close(out3, (Aw[:, 2:2 + Mo].double().t() @ Bw[:, 1:1 + No].double()).float(), 2e-5, "skinny TN strided")
+
+
 # ------------------------------------------------------------------------------- fused BN + LeakyReLU + max pool
 @pytest.mark.parametrize("B,N,C", [(3, 50, 64), (2, 2048, 1024), (5, 333, 132)])
 def test_bn_act_segmax_fused_matches_torch(B, N, C):
