@@ -314,6 +314,61 @@ def run_gpu(args, real_stdout):
                 sys.stderr.write("%-40s x%-3d %8.3f ms  %6.1f TFLOP/s\n" % (
                     key, b[1], b[0], 2.0 * eval(key.split("M=")[1].split()[0]) * eval(key.split("N=")[1].split()[0]) *
                     eval(key.split("K=")[1]) * b[1] / b[0] / 1e9))
+        if os.environ.get("SPGAN_BENCH_BW_TABLE") == "1":          # diagnostic: HBM-bound entry points (stderr)
+            # algorithmic bytes per call from the integer arguments (R or P, C, k ...) of each C-ABI call
+            def nbytes(name, ia):
+                if name in ("spgan_colstats", "spgan_colsum"):
+                    return 4.0 * ia[0] * ia[1]                                   # R, C: one read
+                if name == "spgan_norm_apply":
+                    return 8.0 * ia[0] * ia[1]                                   # read x, write y
+                if name == "spgan_norm_bwd_reduce":
+                    return 8.0 * ia[0] * ia[1]                                   # read g, x
+                if name == "spgan_norm_bwd_apply":
+                    return 12.0 * ia[0] * ia[1]                                  # read g, x, write dx
+                if name in ("spgan_lrelu", "spgan_tanh"):
+                    return 8.0 * ia[-2] if len(ia) >= 2 else None                # n: read + write
+                if name == "spgan_lrelu_bwd":
+                    return 12.0 * ia[-2] if len(ia) >= 2 else None
+                if name == "spgan_bn_softmax_mul_k":
+                    return 16.0 * ia[0] * ia[1] * ia[2]                          # P, k, C: 2 reads, 2 writes
+                if name == "spgan_bn_softmax_mul_k_bwd":
+                    return 20.0 * ia[0] * ia[1] * ia[2]                          # 3 reads, 2 writes
+                if name == "spgan_edge_combine":
+                    return 4.0 * ia[0] * ia[2] * ia[3]                           # P, N, k, C: write E*C (gathers hit L2)
+                if name == "spgan_bn_pool_fwd":
+                    return 4.0 * ia[0] * ia[1]
+                if name == "spgan_bn_pool_bwd":
+                    return 8.0 * ia[0] * ia[1]
+                if name in ("spgan_bn_dbl_bwd_reduce", "spgan_bn_act_dbl_bwd_reduce"):
+                    return 12.0 * ia[0] * ia[1]
+                if name in ("spgan_bn_dbl_bwd_apply", "spgan_bn_act_dbl_bwd_apply"):
+                    return 20.0 * ia[0] * ia[1]
+                if name == "spgan_segmax":
+                    return 4.0 * ia[0] * ia[1]
+                return None
+            bw = {}
+            for name, ia, s_, e_ in prof:
+                try:
+                    nb = nbytes(name, ia)
+                except IndexError:
+                    nb = None
+                if nb:
+                    for key in (name, "%s R=%d C=%d" % (name, ia[0], ia[1]) if name in ("spgan_colstats", "spgan_norm_bwd_reduce") else None):
+                        if key is None:
+                            continue
+                        b = bw.setdefault(key, [0.0, 0.0, 0])
+                        b[0] += nb
+                        b[1] += s_.elapsed_time(e_)
+                        b[2] += 1
+                    continue
+                if nb:
+                    b = bw.setdefault(name, [0.0, 0.0, 0])
+                    b[0] += nb
+                    b[1] += s_.elapsed_time(e_)
+                    b[2] += 1
+            for name, b in sorted(bw.items(), key=lambda kv: -kv[1][1]):
+                sys.stderr.write("BW %-32s x%-3d %8.3f ms %8.2f GB  %7.1f GB/s\n" % (name, b[2], b[1], b[0] / 1e9,
+                                                                                     b[0] / 1e6 / b[1]))
         kernel_share = {k[len("spgan_"):]: round(a[0] / total, 4) for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
         kernel_share["_sum_of_kernel_ms"] = round(total, 3)
         peaks = {}

@@ -167,6 +167,15 @@ int spgan_bn_dbl_bwd_reduce(const float *g, const float *u, const float *x, int6
 int spgan_bn_dbl_bwd_apply(const float *g, const float *u, const float *x, int64_t R, int C, const float *mean,
                            const float *rstd, const float *gamma, const float *sums, float *gg, float *gx,
                            float *ggamma, spgan_stream_t stream);
+/* The same for BatchNorm FUSED with LeakyReLU(slope): g is the gradient w.r.t. the ACTIVATED output; the mask
+ * (slope where fma(xhat, gamma, beta) <= 0) is recomputed from x, applied to g on load and to gg on store
+ * (it is piecewise constant in x, so gx needs no extra term).  C % 4 == 0, 16-byte aligned pointers. */
+int spgan_bn_act_dbl_bwd_reduce(const float *g, const float *u, const float *x, float slope, int64_t R, int C,
+                                const float *mean, const float *rstd, const float *gamma, const float *beta,
+                                float *sums /*[5,C]*/, void *workspace, spgan_stream_t stream);
+int spgan_bn_act_dbl_bwd_apply(const float *g, const float *u, const float *x, float slope, int64_t R, int C,
+                               const float *mean, const float *rstd, const float *gamma, const float *beta,
+                               const float *sums, float *gg, float *gx, float *ggamma, spgan_stream_t stream);
 
 /* ------------------------------------------------------------------ pooling over points / neighbours
  * Max over each segment of seg_rows rows (torch.max(x2, 2) Generator.py:183;

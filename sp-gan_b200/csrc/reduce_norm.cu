@@ -61,13 +61,14 @@ colreduce_partial_kernel(Op op, int C, int64_t seg_rows, int chunks, int64_t row
     }
 }
 
+constexpr int FIN_TY = 16;                // chunk lanes of the finalize block
 template <int NV, typename Fin>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FIN_TY)
 colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
-    // block = 32 columns x 8 chunk lanes of one segment: every partial row is read as one coalesced
-    // 128-byte line per warp; double-precision combine (the chunk order is fixed, so the result is
-    // deterministic)
-    __shared__ double red[8][NV][33];
+    // block = 32 columns x 16 chunk lanes of one segment: every partial row is read as one coalesced 128-byte
+    // line per warp, 8 independent loads in flight per thread (a narrow tensor has up to ~1200 chunk rows and only
+    // C / 32 blocks: the pass is latency-bound); double-precision combine in a fixed order => deterministic
+    __shared__ double red[FIN_TY][NV][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
     for (int64_t seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
@@ -75,9 +76,22 @@ colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, i
 #pragma unroll
         for (int v = 0; v < NV; ++v) s[v] = 0.0;
         if (c < C) {
-            for (int ch = ty; ch < chunks; ch += 8)
+            const float* base = partial + (seg * chunks) * NV * (int64_t)C + c;
+            int ch = ty;
+            for (; ch + 7 * FIN_TY < chunks; ch += 8 * FIN_TY) {
+                float t[8][NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) s[v] += (double)__ldg(partial + (((seg * chunks) + ch) * NV + v) * C + c);
+                for (int q = 0; q < 8; ++q)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) t[q][v] = __ldg(base + ((int64_t)(ch + q * FIN_TY) * NV + v) * C);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) s[v] += (double)t[q][v];
+            }
+            for (; ch < chunks; ch += FIN_TY)
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s[v] += (double)__ldg(base + ((int64_t)ch * NV + v) * C);
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) red[ty][v][tx] = s[v];
@@ -87,7 +101,7 @@ colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, i
             for (int v = 0; v < NV; ++v) {
                 double t = red[0][v][tx];
 #pragma unroll
-                for (int y = 1; y < 8; ++y) t += red[y][v][tx];
+                for (int y = 1; y < FIN_TY; ++y) t += red[y][v][tx];
                 s[v] = t;
             }
             fin(seg, c, s);
@@ -113,6 +127,8 @@ __global__ void colreduce_final_small_kernel(const float* __restrict__ partial, 
     }
 }
 
+// (measured: 24 * 148 blocks is much slower -- chunks of a few dozen rows make the per-block reduction and the
+// finalize pass dominate; 8 * 148 stays)
 constexpr int kReduceTargetBlocks = 8 * kNumSMs;
 
 template <int NV, typename Op, typename Op4, typename Fin>
@@ -144,7 +160,7 @@ int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStrea
     if (chunks <= 8)
         colreduce_final_small_kernel<NV><<<ew_grid(nseg * C, 256), 256, 0, st>>>(partial, C, nseg, chunks, fin);
     else
-        colreduce_final_kernel<NV><<<dim3((unsigned)((C + 31) / 32), (unsigned)(nseg < 4096 ? nseg : 4096)), 256, 0, st>>>(partial, C, nseg, chunks, fin);
+        colreduce_final_kernel<NV><<<dim3((unsigned)((C + 31) / 32), (unsigned)(nseg < 4096 ? nseg : 4096)), 32 * FIN_TY, 0, st>>>(partial, C, nseg, chunks, fin);
     return spgan_launch_status();
 }
 
@@ -336,6 +352,45 @@ struct DblBwdApplyOp4 {
         const float4 t2 = mul4(st.Sgx_r3n, sub4(st.Su_n, ui));
         const float4 gmv = gamma ? ld4(gamma + c4 * 4) : f4(1.f);
         st4(gx + i, mul4(gmv, add4(add4(t0, t1), t2)));
+    }
+};
+// Double backward of train-mode BatchNorm FUSED with LeakyReLU: the activation mask m (slope where the
+// pre-activation is <= 0) is piecewise constant in x, so the closed form of plain BatchNorm applies to
+// g' = m * g, and the cotangent reaching g is m * gg'.  The mask is recomputed from x on the fly.
+struct DblBwdActOp4 {
+    const float* g; const float* u; const float* x; float slope; int C; const float* mean; const float* rstd;
+    const float* gamma; const float* beta;
+    struct State { float4 mean, rstd, gamma, beta; };
+    __device__ State init(int c4, int64_t) const {
+        return State{ld4(mean + c4 * 4), ld4(rstd + c4 * 4), gamma ? ld4(gamma + c4 * 4) : f4(1.f),
+                     beta ? ld4(beta + c4 * 4) : f4(0.f)};
+    }
+    __device__ void accum(const State& st, int64_t r, int c4, float4* acc) const {
+        const int64_t i = r * C + c4 * 4;
+        const float4 ui = ld4(u + i), xm = sub4(ld4(x + i), st.mean);
+        const float4 gi = mask4(ld4(g + i), fma4(mul4(xm, st.rstd), st.gamma, st.beta), slope);
+        acc[0] = add4(acc[0], gi); acc[1] = add4(acc[1], ui); acc[2] = fma4(gi, xm, acc[2]);
+        acc[3] = fma4(ui, xm, acc[3]); acc[4] = fma4(gi, ui, acc[4]);
+    }
+};
+struct DblBwdActApplyOp4 {
+    DblBwdApplyOp4 base; float slope; const float* beta;
+    struct State { DblBwdApplyOp4::State b; float4 rstd, gamma, beta; };
+    __device__ State init(int c4, int64_t seg) const {
+        return State{base.init(c4, seg), ld4(base.rstd + c4 * 4), base.gamma ? ld4(base.gamma + c4 * 4) : f4(1.f),
+                     beta ? ld4(beta + c4 * 4) : f4(0.f)};
+    }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * base.C + c4 * 4;
+        const float4 ui = ld4(base.u + i), xm = sub4(ld4(base.x + i), st.b.mean);
+        const float4 pre = fma4(mul4(xm, st.rstd), st.gamma, st.beta);
+        const float4 gi = mask4(ld4(base.g + i), pre, slope);
+        const float4 ggp = sub4(mul4(st.b.gm_r1, sub4(ui, st.b.Su_n)), mul4(mul4(st.b.gm_r3, xm), st.b.Sux_n));
+        st4(base.gg + i, mask4(ggp, pre, slope));
+        const float4 t0 = mul4(xm, st.b.allsub_r3n);
+        const float4 t1 = mul4(st.b.Sux_r3n, sub4(st.b.Sg_n, gi));
+        const float4 t2 = mul4(st.b.Sgx_r3n, sub4(st.b.Su_n, ui));
+        st4(base.gx + i, mul4(st.gamma, add4(add4(t0, t1), t2)));
     }
 };
 struct AdainApplyOp4 {
@@ -684,32 +739,43 @@ template <bool VEC>
 __global__ void edge_combine_kernel(const float* __restrict__ pc, const float* __restrict__ pn,
                                     const int32_t* __restrict__ idx, const float* __restrict__ bias, int64_t P, int N,
                                     int k, int C, float* __restrict__ out) {
+    // one thread per (point, channel group): the centre terms pc[p] - pn[p] + bias are loaded once and reused
+    // for the k neighbours (k + 2 row loads per k outputs instead of 3k)
     constexpr int W = VEC ? 4 : 1;
     const int Cw = C / W;
-    const int64_t total = P * k * Cw;
+    const int64_t total = P * Cw;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int cw = (int)(i % Cw);
-        const int64_t e = i / Cw;          // edge = p*k + r
-        const int64_t p = e / k;
-        const int64_t j = (p / N) * N + __ldg(idx + e);
+        const int64_t p = i / Cw;
+        const int64_t base = (p / N) * N;
+        const int32_t* ip = idx + p * k;
         if (VEC) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(pn + j * C) + cw);
+            // same operation order as the reference expression (pn[j] - pn[p]) + pc[p] + bias
             const float4 b = __ldg(reinterpret_cast<const float4*>(pn + p * C) + cw);
-            float4 o = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
-            if (pc) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(pc + p * C) + cw);
-                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f), bb = q;
+            if (pc) q = __ldg(reinterpret_cast<const float4*>(pc + p * C) + cw);
+            if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias) + cw);
+            float4* o = reinterpret_cast<float4*>(out) + p * k * Cw + cw;
+#pragma unroll 5
+            for (int r = 0; r < k; ++r) {
+                const int64_t j = base + __ldg(ip + r);
+                const float4 a = __ldg(reinterpret_cast<const float4*>(pn + j * C) + cw);
+                float4 v = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+                if (pc) { v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                if (bias) { v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
+                o[(int64_t)r * Cw] = v;
             }
-            if (bias) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(bias) + cw);
-                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-            }
-            reinterpret_cast<float4*>(out)[i] = o;
         } else {
-            float o = __ldg(pn + j * C + cw) - __ldg(pn + p * C + cw);
-            if (pc) o += __ldg(pc + p * C + cw);
-            if (bias) o += __ldg(bias + cw);
-            out[i] = o;
+            const float b = __ldg(pn + p * C + cw);
+            const float q = pc ? __ldg(pc + p * C + cw) : 0.f;
+            const float bb = bias ? __ldg(bias + cw) : 0.f;
+            for (int r = 0; r < k; ++r) {
+                const int64_t j = base + __ldg(ip + r);
+                float v = __ldg(pn + j * C + cw) - b;
+                if (pc) v += q;
+                if (bias) v += bb;
+                out[(p * k + r) * C + cw] = v;
+            }
         }
     }
 }
@@ -929,6 +995,32 @@ extern "C" int spgan_bn_dbl_bwd_apply(const float* g, const float* u, const floa
     return spgan_launch_status();
 }
 
+extern "C" int spgan_bn_act_dbl_bwd_reduce(const float* g, const float* u, const float* x, float slope, int64_t R,
+                                           int C, const float* mean, const float* rstd, const float* gamma,
+                                           const float* beta, float* sums, void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && u && x && mean && rstd && sums && ws && R >= 1 && C >= 1);
+    if (C % 4 != 0 || !(al16(g) && al16(u) && al16(x) && al16(mean) && al16(rstd) && (!gamma || al16(gamma)) &&
+                        (!beta || al16(beta))))
+        return SPGAN_E_UNSUPPORTED;
+    return run_colreduce<5>(R, C, R, ws, as_stream(s), DblBwdOp{g, u, x, C, mean},
+                            DblBwdActOp4{g, u, x, slope, C, mean, rstd, gamma, beta}, true, Store5Fin{sums, C});
+}
+extern "C" int spgan_bn_act_dbl_bwd_apply(const float* g, const float* u, const float* x, float slope, int64_t R,
+                                          int C, const float* mean, const float* rstd, const float* gamma,
+                                          const float* beta, const float* sums, float* gg, float* gx, float* ggamma,
+                                          spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && u && x && mean && rstd && sums && gg && gx && R >= 1 && C >= 1);
+    if (C % 4 != 0 || !(al16(g) && al16(u) && al16(x) && al16(gg) && al16(gx) && al16(mean) && al16(rstd) &&
+                        al16(sums) && (!gamma || al16(gamma)) && (!beta || al16(beta))))
+        return SPGAN_E_UNSUPPORTED;
+    int rc = fastnorm::run_map(R, C, R, as_stream(s),
+                               DblBwdActApplyOp4{DblBwdApplyOp4{g, u, x, C, 1.f / (float)R, mean, rstd, gamma, sums, gg, gx},
+                                                 slope, beta});
+    if (rc != SPGAN_OK) return rc;
+    if (ggamma) bn_dbl_bwd_gamma_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(C, R, rstd, sums, ggamma);
+    return spgan_launch_status();
+}
+
 extern "C" int spgan_segmax(const float* x, int64_t R, int C, int64_t seg_rows, float* out, int32_t* arg,
                             spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && out && R >= 0 && C >= 1 && seg_rows >= 1 && R % seg_rows == 0);
@@ -1027,8 +1119,8 @@ extern "C" int spgan_edge_combine(const float* pc, const float* pn, const int32_
     SPGAN_CHECK_ARG(pn && idx && out && P >= 0 && N >= 1 && k >= 1 && C >= 1 && P % N == 0);
     if (P == 0) return SPGAN_OK;
     const bool vec = (C % 4 == 0) && al16(pn) && al16(out) && (!pc || al16(pc)) && (!bias || al16(bias));
-    if (vec) edge_combine_kernel<true><<<ew_grid(P * k * (C / 4), 256, 16), 256, 0, as_stream(s)>>>(pc, pn, idx, bias, P, N, k, C, out);
-    else edge_combine_kernel<false><<<ew_grid(P * k * C, 256, 16), 256, 0, as_stream(s)>>>(pc, pn, idx, bias, P, N, k, C, out);
+    if (vec) edge_combine_kernel<true><<<ew_grid(P * (C / 4), 256, 16), 256, 0, as_stream(s)>>>(pc, pn, idx, bias, P, N, k, C, out);
+    else edge_combine_kernel<false><<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(pc, pn, idx, bias, P, N, k, C, out);
     return spgan_launch_status();
 }
 extern "C" int spgan_edge_combine_bwd(const float* g, const int32_t* idx, int64_t P, int N, int k, int C, float* dpc,

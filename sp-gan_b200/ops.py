@@ -558,6 +558,70 @@ class BatchNormTrainBwd(Function):
         return gg, gx, ggamma, None, None
 
 
+class BatchNormActTrain2(Function):
+    """Train-mode BN + LeakyReLU in one pass, TWICE differentiable (the critic under the gradient penalty,
+    gradient_penalty.py:28-33): same forward as BatchNormActTrain; the backward is itself a Function whose backward
+    is the closed-form double backward with the activation mask folded in."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, slope):
+        x = _c(_rows2d(x))
+        R, C = x.shape
+        mean, rstd, var = col_stats(x, R, eps)
+        y = torch.empty_like(x)
+        L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                       slope, y.data_ptr(), _stream())
+        ctx.slope = slope
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, gy, _gm, _gv):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = BatchNormActTrainBwd2.apply(gy, x, gamma, beta, mean, rstd, ctx.slope)
+        if _INPUT_GRAD_ONLY:
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, None, None
+
+
+class BatchNormActTrainBwd2(Function):
+    """(g, x, gamma, beta) -> (dx, dgamma, dbeta) of fused BN + LeakyReLU; backward = double backward for a
+    cotangent on dx (the mask is piecewise constant in x: it multiplies g on the way in and gg on the way out)."""
+
+    @staticmethod
+    def forward(ctx, g, x, gamma, beta, mean, rstd, slope):
+        g = _c(g)
+        ctx.set_materialize_grads(False)
+        dx, sg, sgx = _norm_bwd(g, x, slope, x.shape[0], mean, rstd, gamma, beta)
+        ctx.slope = slope
+        ctx.save_for_backward(g, x, gamma, beta, mean, rstd)
+        return dx, sgx.view(-1), sg.view(-1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u, a, c):
+        g, x, gamma, beta, mean, rstd = ctx.saved_tensors
+        if a is not None or c is not None:
+            raise NotImplementedError("double backward through BatchNorm parameter gradients is not needed by "
+                                      "the WGAN-GP step (only_inputs=True) and is not implemented")
+        if u is None:
+            return None, None, None, None, None, None, None
+        u = _c(u)
+        R, C = x.shape
+        sums = torch.empty((5, C), device=x.device, dtype=torch.float32)
+        L().bn_act_dbl_bwd_reduce(g.data_ptr(), u.data_ptr(), x.data_ptr(), ctx.slope, R, C, mean.data_ptr(),
+                                  rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), sums.data_ptr(),
+                                  _ws(R, C, R, 5, x.device).data_ptr(), _stream())
+        gg = torch.empty_like(x)
+        gx = torch.empty_like(x)
+        ggamma = torch.empty((C,), device=x.device, dtype=torch.float32)
+        L().bn_act_dbl_bwd_apply(g.data_ptr(), u.data_ptr(), x.data_ptr(), ctx.slope, R, C, mean.data_ptr(),
+                                 rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), sums.data_ptr(), gg.data_ptr(),
+                                 gx.data_ptr(), ggamma.data_ptr(), _stream())
+        return gg, gx, ggamma, None, None, None, None
+
+
 class BatchNormActTrain(Function):
     """Fused train-mode BN + LeakyReLU (slope 0 = ReLU); first-order only (generator path)."""
 
@@ -727,12 +791,17 @@ def row_l2_normalize(x, eps):
     return out
 
 
+FUSE_BN_ACT_2ND = _os.environ.get("SPGAN_FUSE_BN_ACT_2ND", "1") != "0"
+
+
 def batch_norm_act(y, bn, slope):
     """nn.BatchNorm{1,2}d (+ LeakyReLU(slope); slope 1 = none) on rows [R, C], honouring bn.training and
     updating the running statistics like the reference modules do in train mode."""
     R = y.shape[0]
     if bn.training or not bn.track_running_stats:
-        if _TWICE_DIFFERENTIABLE:
+        if _TWICE_DIFFERENTIABLE and FUSE_BN_ACT_2ND and slope != 1.0 and y.shape[1] % 4 == 0:
+            z, mean, var = BatchNormActTrain2.apply(y, bn.weight, bn.bias, bn.eps, slope)
+        elif _TWICE_DIFFERENTIABLE:
             z, mean, var = BatchNormTrain.apply(y, bn.weight, bn.bias, bn.eps)
             if slope != 1.0:
                 z = LRelu.apply(z, slope)

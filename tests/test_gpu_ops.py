@@ -165,6 +165,34 @@ def test_batchnorm_train_first_and_second_order(R, C):
     close(b.grad, bc.grad.float(), 1e-4, "dbeta1")
 
 
+@pytest.mark.parametrize("R,C,slope", [(4096, 64, 0.01), (3000, 132, 0.2), (64, 512, 0.01)])
+def test_batchnorm_act_fused_first_and_second_order(R, C, slope):
+    """Twice-differentiable fused BN + LeakyReLU (the critic under the gradient penalty) against torch CPU double
+    precision: y, d/dx with create_graph, and the gradients of a function of that gradient w.r.t. x, gamma and
+    the upstream cotangent."""
+    ops = _ops()
+    x0, g0, b0 = rnd(R, C, seed=25), 1 + 0.2 * rnd(C, seed=26), rnd(C, seed=27)
+    r, r2 = rnd(R, C, seed=28), rnd(R, C, seed=29)
+    xc, gc, bc, rc = (t.double().requires_grad_() for t in (x0, g0, b0, r))
+    yc = F.leaky_relu(_bn_ref(xc, gc, bc), slope)
+    (gxc,) = torch.autograd.grad((yc * rc).sum(), xc, create_graph=True)
+    Lc = (gxc * gxc * r2.double()).sum()
+    Lc.backward()
+
+    x, g, b, rr = (t.cuda().requires_grad_() for t in (x0, g0, b0, r))
+    y, mean, var = ops.BatchNormActTrain2.apply(x, g, b, 1e-5, slope)
+    close(y, yc.float(), 1e-5, "y")
+    (gx,) = torch.autograd.grad(ops.MeanScale.apply(ops.Mul.apply(y, rr), float(R * C)), x, create_graph=True)
+    close(gx, gxc.float(), 1e-4, "dx")
+    Lg = ops.MeanScale.apply(ops.Mul.apply(ops.Mul.apply(gx, gx), r2.cuda()), float(R * C))
+    Lg.backward()
+    close(Lg, Lc.float(), 1e-4, "L")
+    close(x.grad, xc.grad.float(), 5e-4, "ddx")
+    close(g.grad, gc.grad.float(), 5e-4, "ddgamma")
+    close(rr.grad, rc.grad.float(), 5e-4, "dd upstream cotangent")
+    assert b.grad is None or float(b.grad.abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("slope", [0.01, 0.0, 0.2])
 def test_batchnorm_act_fused(slope):
     ops = _ops()
