@@ -392,10 +392,10 @@ def run_gpu(args, real_stdout):
             t_ms = sum(t for _, t in dom) / len(dom)
             fl = gemm_flops(dom[0][0])
             ach = fl / (t_ms / 1e3) / 1e12
-            cap = ncu.get("gemm_tc_kernel<128, 1>", {})
+            cap = next((v for kk, v in ncu.items() if kk.startswith("gemm_tc_kernel<128, 1")), {})
             roofline = {"kernel": "gemm_tc_kernel<128,TF32x3> (tcgen05), critic fc2 forward M=%d N=1024 K=256" % dom[0][0][2],
                         "bound": "tensor", "achieved": ach, "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(),
-                        "traffic": cap.get("dram_traffic_bytes"), "traffic_source": "profiles/ncu_r1.json (ncu --set full, same shape)",
+                        "traffic": cap.get("dram_traffic_bytes"), "traffic_source": "profiles/ncu_r1.json (ncu --set full, same kernel and shape)",
                         "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 4.0 * dom[0][0][2] * (1024 + 256),
                         "launches_per_step": len(dom), "avg_launch_ms": t_ms,
                         "share_of_step": sum(t for _, t in dom) / total,

@@ -9,32 +9,39 @@
 //       twice the MMA rate; NOT used by default because train-mode BatchNorm and the gradient
 //       penalty amplify it to the 1e-3 parity bar (DESIGN.md "GEMM precision").
 //
-// Structure (one persistent CTA per SM, 17 warps):
-//   warps 0-3   epilogue : tcgen05.ld accumulator rows from TMEM -> shared transpose -> (+bias, +C)
-//                          -> 128-byte coalesced global stores
-//   warp  4     MMA      : one lane issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) and commits
-//   warps 5-12  A producer: global fp32 A tile -> split -> 128B-swizzled K-major shared tiles, with
-//                          the next k-block's loads in flight during conversion.  (No TMA: the A
-//                          operand needs the fp32 -> 2 x bf16 conversion on the way in.)
-//   warps 13-16 B loader : pre-split weight tiles -> shared with cp.async (from L2), two stages in flight
+// Structure (one persistent CTA per SM, 20 warps):
+//   warps 0-7   epilogue : tcgen05.ld accumulator rows from TMEM -> shared transpose -> (+bias, +C)
+//                          -> 128-byte coalesced global stores (two warps per TMEM lane quarter)
+//   warp  8     MMA      : one lane issues tcgen05.mma (M=128, N=BN, K=8 tf32 / 16 bf16) and commits
+//   warps 9-16  A producer: global fp32 A tile -> split -> 128B-swizzled K-major shared tiles, with
+//                          the next k-blocks' loads in flight during conversion.  (No TMA: the A
+//                          operand needs the fp32 -> hi/lo conversion on the way in.)
+//   warps 17-19 B loader : pre-split weight tiles -> shared with cp.async (from L2), two stages in flight
 // Pipelines: full/empty mbarriers per shared stage, tmem_full/tmem_empty per accumulator buffer
 // (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
 // Every mbarrier wait is bounded; on timeout the kernel raises a status word instead of hanging.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 // one k-block = one 128-byte swizzle row per matrix row: 64 bf16 or 32 tf32 elements
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int MMA_WARP = 4;
-constexpr int A_WARP0 = 5;                  // 8 warps convert the fp32 A operand
+constexpr int NUM_EPI_WARPS = 8;            // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int MMA_WARP = 8;
+constexpr int A_WARP0 = 9;                  // 8 warps convert the fp32 A operand
 constexpr int NUM_A_THREADS = 8 * 32;
-constexpr int B_WARP0 = 13;                 // 4 warps stream the pre-split B operand (cp.async, 2 stages in flight)
-constexpr int NUM_B_THREADS = 4 * 32;
-constexpr int TC_THREADS = 17 * 32;         // 544
-constexpr int EPI_LD = 36;                  // padded row stride (floats) of the epilogue staging tile
+constexpr int B_WARP0 = 17;                 // 3 warps stream the pre-split B operand (cp.async, 2 stages in flight)
+constexpr int NUM_B_THREADS = 3 * 32;
+constexpr int TC_THREADS = 20 * 32;         // 640: the register file allows 96 registers per thread
+constexpr int EPI_LD = 32;                  // epilogue staging tile: 32 x 32 floats per warp, XOR-swizzled float4 columns
+#ifndef SPGAN_TC_PF_DEFAULT
+#define SPGAN_TC_PF_DEFAULT 3
+#endif
+#ifndef SPGAN_TC_CONSUMER_FENCE_DEFAULT
+#define SPGAN_TC_CONSUMER_FENCE_DEFAULT 0
+#endif
 
 template <int BN, bool TF32>
 struct Cfg {
@@ -49,7 +56,7 @@ struct Cfg {
     // this cuts that count by 3 (measured: rms error ~7e-9*K -> ~2.4e-9*K).
     static constexpr int NACC = TF32 ? 2 : 1;
     static constexpr int TMEM_COLS = 2 * NACC * BN;      // two tile buffers; power of two <= 512
-    static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * 36 * 4;
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
                                       EPI_BYTES /*epilogue staging*/;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -93,7 +100,12 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int BN, bool TF32>
+// CF ("consumer fence"): where the generic->async proxy fence for the operand tiles is executed.  false: by every
+// producer thread before its mbarrier arrive (the textbook placement).  true: once per k-block by the MMA-issuing
+// thread after its acquire of the full barrier.  fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and
+// the MEMBAR makes a producer wait for ITS OWN outstanding global prefetch loads: with the fence on the producer
+// side every k-block costs a full memory latency no matter how deep the prefetch ring is.
+template <int BN, bool TF32, int PF, bool CF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
                const unsigned char* __restrict__ Bhi, const unsigned char* __restrict__ Blo, int Kp, int n_tiles,
@@ -146,8 +158,11 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         constexpr int TASKS = BM * 8 / NUM_A_THREADS;          // 4 (row, 16-byte chunk) tasks per thread
         constexpr int V = TF32 ? 1 : 2;                        // float4 loads per task
         const int ptid = tid - A_WARP0 * 32;
-        float4 cur[V * TASKS], nxt[V * TASKS];
-        // loop invariants of this thread's tasks: swizzled shared offset and column offset inside a k-block
+        // PF register sets form a ring: PF-1 k-blocks of loads are in flight while one is converted.  (The first
+        // version kept two named sets and copied nxt -> cur at the end of every iteration: that copy waits for
+        // the loads it reads, so the NEXT loads could only be issued after the previous ones had landed -- one
+        // k-block in flight per SM, ~1 TB/s of A traffic on K <= 128 shapes.)
+        float4 buf[PF][V * TASKS];
         uint32_t soff[TASKS];
         int colo[TASKS];
         const float* rowp[TASKS];                              // row pointers of the tile being LOADED
@@ -185,36 +200,46 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         };
         int stage = 0;
         uint32_t phase = 0;
-        // the load cursor (lmt, lnt, lkb) runs one k-block ahead of the convert cursor
+        // the load cursor (lmt, lnt, lkb) runs PF-1 k-blocks ahead of the convert cursor, across tile boundaries;
+        // `ahead` = k-blocks loaded but not yet converted
         int lmt = mt0, lnt = nt0, lkb = 0;
-        bool have = lmt < m_tiles;
-        if (have) { set_rows(lmt); load_a(0, cur); }
-        while (have) {
+        bool lvalid = lmt < m_tiles;
+        if (lvalid) set_rows(lmt);
+        auto advance = [&]() {
             if (++lkb == KB) { lkb = 0; tile_next(lmt, lnt); if (lmt < m_tiles) set_rows(lmt); }
-            const bool have_next = lmt < m_tiles;
-            if (have_next) load_a(lkb, nxt);
-            if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) break;
-            unsigned char* sa_hi = smem + stage * cfg::STAGE_BYTES;
-            unsigned char* sa_lo = sa_hi + cfg::A_BYTES;
+            lvalid = lmt < m_tiles;
+        };
+        int ahead = 0;
 #pragma unroll
-            for (int j = 0; j < TASKS; ++j) {
-                uint4 hi, lo;
-                if constexpr (TF32) {
-                    split4_tf32(cur[j], hi, lo);
-                } else {
-                    const float v[8] = {cur[2 * j].x, cur[2 * j].y, cur[2 * j].z, cur[2 * j].w,
-                                        cur[2 * j + 1].x, cur[2 * j + 1].y, cur[2 * j + 1].z, cur[2 * j + 1].w};
-                    split8(v, hi, lo);
+        for (int s = 0; s < PF - 1; ++s)
+            if (lvalid) { load_a(lkb, buf[s]); ++ahead; advance(); }
+        bool done = (ahead == 0);
+        while (!done) {
+#pragma unroll
+            for (int s = 0; s < PF; ++s) {
+                if (ahead == 0) { done = true; break; }
+                if (lvalid) { load_a(lkb, buf[(s + PF - 1) % PF]); ++ahead; advance(); }
+                if (!mbar_wait(empty_bar(stage), phase ^ 1, vstatus)) { done = true; break; }
+                unsigned char* sa_hi = smem + stage * cfg::STAGE_BYTES;
+                unsigned char* sa_lo = sa_hi + cfg::A_BYTES;
+#pragma unroll
+                for (int j = 0; j < TASKS; ++j) {
+                    uint4 hi, lo;
+                    if constexpr (TF32) {
+                        split4_tf32(buf[s][j], hi, lo);
+                    } else {
+                        const float v[8] = {buf[s][2 * j].x, buf[s][2 * j].y, buf[s][2 * j].z, buf[s][2 * j].w,
+                                            buf[s][2 * j + 1].x, buf[s][2 * j + 1].y, buf[s][2 * j + 1].z, buf[s][2 * j + 1].w};
+                        split8(v, hi, lo);
+                    }
+                    *reinterpret_cast<uint4*>(sa_hi + soff[j]) = hi;
+                    *reinterpret_cast<uint4*>(sa_lo + soff[j]) = lo;
                 }
-                *reinterpret_cast<uint4*>(sa_hi + soff[j]) = hi;
-                *reinterpret_cast<uint4*>(sa_lo + soff[j]) = lo;
+                if constexpr (!CF) fence_proxy_async();      // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(full_bar(stage));
+                if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+                --ahead;
             }
-            fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core
-            mbar_arrive(full_bar(stage));
-            if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
-#pragma unroll
-            for (int j = 0; j < V * TASKS; ++j) cur[j] = nxt[j];
-            have = have_next;
         }
     } else if (warp >= B_WARP0) {
         // ================================================================ B loaders (pre-split, cp.async)
@@ -224,7 +249,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         int stage = 0, prev_stage = -1;
         uint32_t phase = 0;
         bool ok = true;
-        constexpr int BT = BN * 8 / NUM_B_THREADS;            // tasks per thread
+        constexpr int BT = (BN * 8 + NUM_B_THREADS - 1) / NUM_B_THREADS;      // tasks per thread (last one guarded)
         const uint32_t row_bytes = (uint32_t)Kp * ESZ;
         for (int mt = mt0, nt = nt0; mt < m_tiles && ok; tile_next(mt, nt)) {
             const uint32_t tile_off = (uint32_t)(nt * BN) * row_bytes;          // 32-bit: B is at most a few MB
@@ -236,6 +261,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
 #pragma unroll
                 for (int j = 0; j < BT; ++j) {
                     const int task = ptid + j * NUM_B_THREADS;
+                    if (task >= BN * 8) break;
                     const int row = task >> 3, ch = task & 7;
                     const uint32_t e = k_off + (uint32_t)row * row_bytes + (uint32_t)(ch * CHUNK) * ESZ;
                     const uint32_t off = swz(row, ch);
@@ -245,7 +271,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (prev_stage >= 0) {
                     asm volatile("cp.async.wait_group 1;" ::: "memory");      // the previous stage has landed
-                    fence_proxy_async();
+                    if constexpr (!CF) fence_proxy_async();
                     mbar_arrive(full_bar(prev_stage));
                 }
                 prev_stage = stage;
@@ -254,7 +280,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         }
         if (prev_stage >= 0) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            fence_proxy_async();
+            if constexpr (!CF) fence_proxy_async();
             if (ok) mbar_arrive(full_bar(prev_stage));
         }
     } else if (warp == MMA_WARP) {
@@ -273,6 +299,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                 if (!mbar_wait(full_bar(stage), phase, vstatus)) { ok = false; break; }
                 tc_fence_after();
                 if (lane == 0) {
+                    if constexpr (CF) fence_proxy_async();        // acquired the producers' writes: hand them to the async proxy
                     const uint32_t sa_hi = smem_u32(smem + stage * cfg::STAGE_BYTES);
                     const uint32_t sa_lo = sa_hi + cfg::A_BYTES;
                     const uint32_t sb_hi = sa_lo + cfg::A_BYTES;
@@ -307,43 +334,54 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
             if (acc == 0) acc_phase ^= 1;
         }
     } else {
-        // ================================================================ epilogue (warps 0..3)
-        // TMEM gives each thread one accumulator row; 32x32 blocks go through a padded shared tile so
-        // that global stores are 128-byte contiguous per row (8 lanes x float4).
+        // ================================================================ epilogue (warps 0..7)
+        // TMEM gives each thread one accumulator row (a warp can only read the lane quarter warp % 4); 32x32
+        // blocks go through a swizzled shared tile so that global stores are 128-byte contiguous per row
+        // (8 lanes x float4).  Warps w and w + 4 share a lane quarter and alternate 32-column chunks: with K <= 128
+        // the epilogue, not the MMAs, paces the kernel (measured: the MMA warp spent ~60 % of its time waiting for
+        // a free accumulator with 4 epilogue warps).
+        const int quarter = warp & 3, half = warp >> 2;
         float* T = epi_smem + warp * (32 * EPI_LD);
         int acc = 0;
         uint32_t acc_phase = 0;
         bool ok = true;
         for (int mt = mt0, nt = nt0; mt < m_tiles && ok; tile_next(mt, nt)) {
-            const int64_t m0 = (int64_t)mt * BM + warp * 32;
+            const int64_t m0 = (int64_t)mt * BM + quarter * 32;
             const int n0 = nt * BN;
             if (!mbar_wait(tfull_bar(acc), acc_phase, vstatus)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * cfg::NACC * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * cfg::NACC * BN);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 float v[32];
-                tmem_ld16(taddr + c0, v);               // all lanes participate (sync.aligned)
-                tmem_ld16(taddr + c0 + 16, v + 16);
-                if constexpr (TF32) {                   // add the cross-term accumulator
-                    float w[32];
-                    tmem_ld16(taddr + BN + c0, w);
-                    tmem_ld16(taddr + BN + c0 + 16, w + 16);
+                {
+                    uint32_t rv[32], rw[32];
+                    tmem_ld32_issue(taddr + c0, rv);    // all lanes participate (sync.aligned); one wait for both
+                    if constexpr (TF32) tmem_ld32_issue(taddr + BN + c0, rw);     // cross-term accumulator
+                    tmem_ld_wait();
+                    tmem_pin32(rv);
+                    if constexpr (TF32) {
+                        tmem_pin32(rw);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += w[j];
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]) + __uint_as_float(rw[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * (q ^ (lane & 7))) =
+                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
                 if (n0 + c0 < N) {
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
-                        const int r = rr * 4 + (lane >> 3), cq = (lane & 7) * 4;
+                        const int r = rr * 4 + (lane >> 3), g = lane & 7, cq = g * 4;
                         const int64_t row = m0 + r;
                         const int col = n0 + c0 + cq;
                         if (row < M && col < N) {
-                            float4 o = *reinterpret_cast<const float4*>(T + r * EPI_LD + cq);
+                            float4 o = *reinterpret_cast<const float4*>(T + r * EPI_LD + 4 * (g ^ (r & 7)));
                             float* cp = C + row * ldc + col;
                             if (vecC && col + 4 <= N) {
                                 if (bias) {
@@ -415,11 +453,11 @@ __global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-template <int BN, bool TF32>
-int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const unsigned char* hi, const unsigned char* lo,
-              int Kp, int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
+template <int BN, bool TF32, int PF, bool CF>
+int launch_tc_pf(int64_t M, int N, int K, const float* A, int64_t lda, const unsigned char* hi, const unsigned char* lo,
+                 int Kp, int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
     using cfg = Cfg<BN, TF32>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, PF, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = Npad / BN;
@@ -427,10 +465,45 @@ int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const unsign
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
     const bool vecA = (lda % 4 == 0) && aligned16(A);
     const bool vecC = (ldc % 4 == 0) && aligned16(C) && (bias == nullptr || aligned16(bias));
-    gemm_tc_kernel<BN, TF32><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc,
-                                                                         bias, accumulate, status, vecA, vecC);
+    gemm_tc_kernel<BN, TF32, PF, CF><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc,
+                                                                             bias, accumulate, status, vecA, vecC);
     return spgan_launch_status();
 }
+
+// A-producer prefetch depth (register sets): SPGAN_TC_PF = 2 | 3 | 4 overrides the default (tuning knob)
+inline int tc_prefetch_sets() {
+    static const int pf = [] {
+        const char* e = getenv("SPGAN_TC_PF");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 2 && v <= 4) ? v : SPGAN_TC_PF_DEFAULT;
+    }();
+    return pf;
+}
+
+// SPGAN_TC_FENCE = producer | consumer overrides where the proxy fence runs (see gemm_tc_kernel)
+inline bool tc_consumer_fence() {
+    static const bool cf = [] {
+        const char* e = getenv("SPGAN_TC_FENCE");
+        if (e && e[0] == 'p') return false;
+        if (e && e[0] == 'c') return true;
+        return SPGAN_TC_CONSUMER_FENCE_DEFAULT != 0;
+    }();
+    return cf;
+}
+
+#define SPGAN_TC_ARGS M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st
+template <int BN, bool TF32>
+int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const unsigned char* hi, const unsigned char* lo,
+              int Kp, int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
+    const bool cf = tc_consumer_fence();
+    if constexpr (TF32) {
+        const int pf = tc_prefetch_sets();
+        if (pf == 3) return cf ? launch_tc_pf<BN, TF32, 3, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, TF32, 3, false>(SPGAN_TC_ARGS);
+        if (pf == 4) return cf ? launch_tc_pf<BN, TF32, 4, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, TF32, 4, false>(SPGAN_TC_ARGS);
+    }
+    return cf ? launch_tc_pf<BN, TF32, 2, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, TF32, 2, false>(SPGAN_TC_ARGS);
+}
+#undef SPGAN_TC_ARGS
 
 template <bool TF32>
 int run_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,

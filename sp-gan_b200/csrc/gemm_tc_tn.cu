@@ -246,16 +246,20 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32], w[32];
-                tmem_ld16(taddr + c0, v);
-                tmem_ld16(taddr + c0 + 16, v + 16);
-                tmem_ld16(taddr + BN + c0, w);
-                tmem_ld16(taddr + BN + c0 + 16, w + 16);
+                float v[32];
+                {
+                    uint32_t rv[32], rw[32];
+                    tmem_ld32_issue(taddr + c0, rv);              // main and cross-term accumulators: one wait
+                    tmem_ld32_issue(taddr + BN + c0, rw);
+                    tmem_ld_wait();
+                    tmem_pin32(rv);
+                    tmem_pin32(rw);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]) + __uint_as_float(rw[j]);
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * q) =
-                        make_float4(v[4 * q] + w[4 * q], v[4 * q + 1] + w[4 * q + 1], v[4 * q + 2] + w[4 * q + 2],
-                                    v[4 * q + 3] + w[4 * q + 3]);
+                    *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
                 if (n0 + c0 < No) {
 #pragma unroll
