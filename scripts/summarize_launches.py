@@ -22,7 +22,7 @@ def main(path, out):
         ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
         for r in rd:
             rows.append((r[ki], float(r[vi].replace(",", "")), r[gi], r[bi]))
-    adam = [i for i, r in enumerate(rows) if "adam_kernel" in r[0]]
+    adam = [i for i, r in enumerate(rows) if "adam_kernel" in r[0] or "adam_dev_kernel" in r[0]]
     if len(adam) >= 4:
         lo, hi = adam[-3] + 1, adam[-1] + 1          # last full step: after the previous step's G-phase Adam
     else:
