@@ -67,6 +67,44 @@ int spgan_group(const float *x_bcn, const int32_t *idx, int B, int C, int N, int
 int spgan_idx32_to_idx64(const int32_t *src, int64_t *dst, int64_t n, spgan_stream_t stream);
 int spgan_idx64_to_idx32(const int64_t *src, int32_t *dst, int64_t n, spgan_stream_t stream);
 
+/* ------------------------------------------------------------------ the other kNN / grouping entry points
+ *  that share the hot path's distance arithmetic.  Query and candidate clouds are
+ * channel-first [B,C,Nq] / [B,C,Nc] with caller-supplied squared norms (spgan_sqnorm for the
+ * channel-first reduction order of modules.py:642/697, spgan_sqnorm_rows for point-major rows).
+ * dist(i,j) = (-2*dot + a) + b with (a,b) = (|q_i|^2, |c_j|^2), or (|c_j|^2, |q_i|^2) when
+ * cand_norm_first != 0 (the rounding order of `knn`, modules.py:641-643).  Ties: (dist, index). */
+
+/* xs[r] = sum_c x[r,c]^2 of point-major rows [R,C], rounded squares added in channel order
+ * (Common/pointnet_util.py:38-39; bit-identical to torch CPU for C <= 3, i.e. xyz rows). */
+int spgan_sqnorm_rows(const float *x_rows, int64_t R, int C, float *xs, spgan_stream_t stream);
+
+/* idx[b,i,r] = candidate of rank first_rank + r (ascending distance) for query i; int32 [B,Nq,k],
+ * first_rank in {0,1}, k + first_rank <= min(Nc, 32).  Replaces the distance + topk/sort of
+ * `knn` (modules.py:640-646, Common/ops.py:129-135; first_rank 0, cand_norm_first 1) and
+ * `knn_point` (Common/pointnet_util.py, Common/pointconv_util.py:107-118; first_rank 0). */
+int spgan_knn_query(const float *xq_bcn, const float *xsq, int Nq, const float *xc_bcn, const float *xsc, int Nc,
+                    int B, int C, int k, int first_rank, int cand_norm_first, int32_t *idx, spgan_stream_t stream);
+
+/* dist[B,Nq,Nc] materialised: `pairwise_dist` (modules.py:629-637), `square_distance`
+ * (Common/pointnet_util.py:19-40). */
+int spgan_pairwise_sqdist(const float *xq_bcn, const float *xsq, int Nq, const float *xc_bcn, const float *xsc,
+                          int Nc, int B, int C, int cand_norm_first, float *dist, spgan_stream_t stream);
+
+/* spgan_group with a selectable channel order: diff_first != 0 writes [neighbour - centre, centre]
+ * (`get_graph_feature`, modules.py:678), 0 writes [centre, neighbour - centre] (modules.py:720). */
+int spgan_group_ex(const float *x_bcn, const int32_t *idx, int B, int C, int N, int k, int diff_first, float *ee,
+                   spgan_stream_t stream);
+
+/* out[b,s,:] = points[b, idx[b,s], :] for points [B,N,C], idx [B,S] (int32, or int64 when
+ * idx_is_int64 != 0): `index_points` (Common/pointnet_util.py:43-59).  If status != NULL it is set
+ * to 1 when an index falls outside [-N,N) (that row of out is left untouched; negative indices
+ * wrap like torch fancy indexing).
+ * spgan_scatter_add_rows is its adjoint: dpoints[b, idx[b,s], :] += g[b,s,:] (atomic). */
+int spgan_gather_rows(const float *points, const void *idx, int idx_is_int64, int B, int N, int64_t S, int C,
+                      float *out, int *status, spgan_stream_t stream);
+int spgan_scatter_add_rows(const float *g, const void *idx, int idx_is_int64, int B, int N, int64_t S, int C,
+                           float *dpoints, spgan_stream_t stream);
+
 /* ------------------------------------------------------------------ layout
  * [B,C,N] (arbitrary element strides sb, sc, sn) <-> point-major rows [B*N, C].
  * Replaces the transpose/contiguous calls of Generator.py:167,170 and the strided read of

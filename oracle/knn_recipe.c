@@ -197,3 +197,68 @@ int spgan_oracle_knn(const float *x, int B, int C, int N, int k, int32_t *idx, f
     free(xs); free(bd); free(bi); free(xi_col);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------
+ * The reference's other distance entry points: two clouds, either norm order.
+ *   knn            Generation/modules.py:640-646   pd = -xx - inner - xx^T   (candidate norm first, negated)
+ *   pairwise_dist  Generation/modules.py:629-637   dist = xy + xx + yy^T     (query norm first)
+ *   square_distance Common/pointnet_util.py:19-40  dist = -2 src.dst^T; += |src|^2; += |dst|^2
+ * xq: [B, C, Nq], xc: [B, C, Nc] channel-first; xsq [B, Nq], xsc [B, Nc] squared norms supplied by the caller
+ * (the reduction order of the norms depends on the memory layout the reference reduces over).
+ * dist: [B, Nq, Nc].  The dot product is the same FMA chain over channels as above. */
+void spgan_oracle_dist2(const float *xq, const float *xsq, int Nq, const float *xc, const float *xsc, int Nc,
+                        int B, int C, int cand_norm_first, float *dist) {
+    for (int b = 0; b < B; ++b) {
+        const float *qb = xq + (int64_t)b * C * Nq;
+        const float *cb = xc + (int64_t)b * C * Nc;
+        for (int i = 0; i < Nq; ++i)
+            for (int j = 0; j < Nc; ++j) {
+                float dot = 0.f;
+                for (int c = 0; c < C; ++c) dot = fmaf(qb[(int64_t)c * Nq + i], cb[(int64_t)c * Nc + j], dot);
+                const float m2 = -2.0f * dot;
+                const float nq = xsq[(int64_t)b * Nq + i], nc = xsc[(int64_t)b * Nc + j];
+                float d;
+                if (cand_norm_first) { const float t = m2 + nc; d = t + nq; }
+                else { const float t = m2 + nq; d = t + nc; }
+                dist[((int64_t)b * Nq + i) * Nc + j] = d;
+            }
+    }
+}
+
+/* Point-major squared norms, rounded squares added in channel order (what torch CPU computes for
+ * `torch.sum(src ** 2, -1)` on xyz rows, C <= 3). */
+void spgan_oracle_sqnorm_rows(const float *x, int64_t R, int C, float *xs) {
+    for (int64_t r = 0; r < R; ++r) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float v = x[r * C + c];
+            const float sq = v * v;
+            acc = acc + sq;
+        }
+        xs[r] = acc;
+    }
+}
+
+/* Ranks first_rank .. first_rank+k-1 of every row of a [R, Nc] distance matrix in ascending (dist, j) order.
+ * idx: [R, k] int32.  Returns 0, or -1 on bad arguments. */
+int spgan_oracle_topk_rows(const float *dist, int64_t R, int Nc, int k, int first_rank, int32_t *idx) {
+    if (R < 0 || Nc < 1 || k < 1 || first_rank < 0 || k + first_rank > Nc) return -1;
+    const int K1 = k + first_rank;
+    float *bd = (float *)malloc(sizeof(float) * (size_t)K1);
+    int32_t *bi = (int32_t *)malloc(sizeof(int32_t) * (size_t)K1);
+    for (int64_t r = 0; r < R; ++r) {
+        int cnt = 0;
+        for (int j = 0; j < Nc; ++j) {
+            const float d = dist[r * Nc + j];
+            if (cnt == K1 && !(d < bd[K1 - 1])) continue;
+            int pos = (cnt < K1) ? cnt : K1 - 1;
+            while (pos > 0 && d < bd[pos - 1]) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; --pos; }
+            bd[pos] = d;
+            bi[pos] = j;
+            if (cnt < K1) ++cnt;
+        }
+        for (int t = 0; t < k; ++t) idx[r * k + t] = bi[t + first_rank];
+    }
+    free(bd); free(bi);
+    return 0;
+}

@@ -38,6 +38,13 @@ def _load():
         lib.spgan_oracle_knn.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ip, fp]
         lib.spgan_oracle_knn.restype = ctypes.c_int
+        lib.spgan_oracle_dist2.argtypes = [fp, fp, ctypes.c_int, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, fp]
+        lib.spgan_oracle_dist2.restype = None
+        lib.spgan_oracle_sqnorm_rows.argtypes = [fp, ctypes.c_int64, ctypes.c_int, fp]
+        lib.spgan_oracle_sqnorm_rows.restype = None
+        lib.spgan_oracle_topk_rows.argtypes = [fp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ip]
+        lib.spgan_oracle_topk_rows.restype = ctypes.c_int
         _lib = lib
     return _lib
 
@@ -81,6 +88,41 @@ def knn(x, k, return_dist=False):
     if rc != 0:
         raise ValueError("spgan_oracle_knn: bad arguments (need 1 <= k < N)")
     return (idx, kd) if return_dist else idx
+
+
+def dist2(xq, xsq, xc, xsc, cand_norm_first=False):
+    """[B, Nq, Nc] distances between two channel-first clouds, (-2 q.c + first norm) + second norm, with the
+    caller's squared norms (modules.py:629-646, pointnet_util.py:19-40)."""
+    xq, xc = _f32(xq), _f32(xc)
+    xsq = np.ascontiguousarray(xsq, np.float32)
+    xsc = np.ascontiguousarray(xsc, np.float32)
+    B, C, Nq = xq.shape
+    Nc = xc.shape[2]
+    out = np.empty((B, Nq, Nc), np.float32)
+    _load().spgan_oracle_dist2(_ptr(xq, ctypes.c_float), _ptr(xsq, ctypes.c_float), Nq, _ptr(xc, ctypes.c_float),
+                               _ptr(xsc, ctypes.c_float), Nc, B, C, int(bool(cand_norm_first)),
+                               _ptr(out, ctypes.c_float))
+    return out
+
+
+def sqnorm_rows(p):
+    """|p[b, n, :]|^2 of point-major rows [B, N, C], rounded squares added in channel order."""
+    p = np.ascontiguousarray(p, np.float32)
+    B, N, C = p.shape
+    out = np.empty((B, N), np.float32)
+    _load().spgan_oracle_sqnorm_rows(_ptr(p, ctypes.c_float), B * N, C, _ptr(out, ctypes.c_float))
+    return out
+
+
+def topk_rows(dist, k, first_rank=0):
+    """Ranks first_rank..first_rank+k-1 of every row of dist [..., Nc] in ascending (dist, index) order."""
+    dist = np.ascontiguousarray(dist, np.float32)
+    Nc = dist.shape[-1]
+    R = dist.size // Nc
+    idx = np.empty(dist.shape[:-1] + (k,), np.int32)
+    if _load().spgan_oracle_topk_rows(_ptr(dist, ctypes.c_float), R, Nc, k, first_rank, _ptr(idx, ctypes.c_int32)):
+        raise ValueError("spgan_oracle_topk_rows: bad arguments")
+    return idx
 
 
 def idx_equal_up_to_ties(idx_a, idx_b, kdist):

@@ -1143,15 +1143,20 @@ def idx_to_int32(idx64):
 
 class Group(Function):
     """ee[B, 2C, N, k] = cat(centre, neighbour - centre) for a given neighbour list
-    (modules.py:706-720); backward scatters with the edge-aggregation kernel."""
+    (modules.py:706-720), or cat(neighbour - centre, centre) with diff_first (get_graph_feature,
+    modules.py:678); backward scatters with the edge-aggregation kernel."""
 
     @staticmethod
-    def forward(ctx, x, idx32, k):
+    def forward(ctx, x, idx32, k, diff_first=False):
         x = _c(x)
         B, C, N = x.shape
         ee = torch.empty((B, 2 * C, N, k), device=x.device, dtype=torch.float32)
-        L().group(x.data_ptr(), idx32.data_ptr(), B, C, N, k, ee.data_ptr(), _stream())
+        if diff_first:
+            L().group_ex(x.data_ptr(), idx32.data_ptr(), B, C, N, k, 1, ee.data_ptr(), _stream())
+        else:
+            L().group(x.data_ptr(), idx32.data_ptr(), B, C, N, k, ee.data_ptr(), _stream())
         ctx.dims = (B, C, N, k)
+        ctx.diff_first = bool(diff_first)
         ctx.save_for_backward(idx32)
         return ee
 
@@ -1167,8 +1172,8 @@ class Group(Function):
         g3 = g.view(B, 2 * C, N * k)
         L().bcn_to_rows(g3.data_ptr(), g3.stride(0), g3.stride(1), g3.stride(2), B, 2 * C, N * k, rows.data_ptr(),
                         _stream())
-        g_ctr = contiguous(rows[:, :C])
-        g_dif = contiguous(rows[:, C:])
+        g_ctr = contiguous(rows[:, C:] if ctx.diff_first else rows[:, :C])
+        g_dif = contiguous(rows[:, :C] if ctx.diff_first else rows[:, C:])
         dpc = torch.empty((B * N, C), device=g.device, dtype=torch.float32)
         dpn = torch.empty((B * N, C), device=g.device, dtype=torch.float32)
         junk = torch.empty((B * N, C), device=g.device, dtype=torch.float32)
@@ -1178,7 +1183,78 @@ class Group(Function):
         L().axpby(1.0, dpc.data_ptr(), 1.0, dpn.data_ptr(), junk.data_ptr(), dpc.numel(), _stream())
         dx = torch.empty((B, C, N), device=g.device, dtype=torch.float32)
         L().rows_to_bcn(junk.data_ptr(), B, C, N, dx.data_ptr(), _stream())
-        return dx, None, None
+        return dx, None, None, None
+
+
+# =========================================================================================
+# the other kNN / grouping entry points: raw operators, wrapped in pointnet_util.py
+# =========================================================================================
+def sqnorm_bcn(x_bcn, main_cols=-1):
+    """|x[b,:,n]|^2 of a contiguous [B, C, N] tensor in the channel-first reduction order (modules.py:642,697)."""
+    B, C, N = x_bcn.shape
+    xs = torch.empty((B, N), device=x_bcn.device, dtype=torch.float32)
+    L().sqnorm(x_bcn.data_ptr(), B, C, N, main_cols, xs.data_ptr(), _stream())
+    return xs
+
+
+def sqnorm_rows(p_bnc):
+    """|p[b,n,:]|^2 of contiguous point-major rows [B, N, C] (pointnet_util.py:38-39)."""
+    B, N, C = p_bnc.shape
+    xs = torch.empty((B, N), device=p_bnc.device, dtype=torch.float32)
+    L().sqnorm_rows(p_bnc.data_ptr(), B * N, C, xs.data_ptr(), _stream())
+    return xs
+
+
+def knn_query(xq_bcn, xsq, xc_bcn, xsc, k, first_rank, cand_norm_first):
+    """-> idx int32 [B, Nq, k]: ranks first_rank .. first_rank+k-1 of every query's ascending distance row."""
+    B, C, Nq = xq_bcn.shape
+    Nc = xc_bcn.shape[2]
+    idx = torch.empty((B, Nq, k), device=xq_bcn.device, dtype=torch.int32)
+    L().knn_query(xq_bcn.data_ptr(), xsq.data_ptr(), Nq, xc_bcn.data_ptr(), xsc.data_ptr(), Nc, B, C, k,
+                  int(first_rank), int(bool(cand_norm_first)), idx.data_ptr(), _stream())
+    return idx
+
+
+def pairwise_sqdist(xq_bcn, xsq, xc_bcn, xsc, cand_norm_first=False):
+    """-> dist fp32 [B, Nq, Nc], (-2 q.c + first norm) + second norm."""
+    B, C, Nq = xq_bcn.shape
+    Nc = xc_bcn.shape[2]
+    out = torch.empty((B, Nq, Nc), device=xq_bcn.device, dtype=torch.float32)
+    L().pairwise_sqdist(xq_bcn.data_ptr(), xsq.data_ptr(), Nq, xc_bcn.data_ptr(), xsc.data_ptr(), Nc, B, C,
+                        int(bool(cand_norm_first)), out.data_ptr(), _stream())
+    return out
+
+
+class GatherRows(Function):
+    """out[b, s, :] = points[b, idx[b, s], :] (index_points, pointnet_util.py:43-59); backward scatter-adds."""
+
+    @staticmethod
+    def forward(ctx, points, idx):
+        points = _c(points, "points")
+        if idx.dtype not in (torch.int32, torch.int64) or not idx.is_cuda:
+            raise RuntimeError("spgan_b200: idx must be a CUDA int32/int64 tensor")
+        idx = idx.contiguous()
+        B, N, C = points.shape
+        S = idx.numel() // max(B, 1)
+        out = torch.empty((B, S, C), device=points.device, dtype=torch.float32)
+        status = torch.zeros(1, device=points.device, dtype=torch.int32)
+        L().gather_rows(points.data_ptr(), idx.data_ptr(), int(idx.dtype == torch.int64), B, N, S, C, out.data_ptr(),
+                        status.data_ptr(), _stream())
+        ctx.dims = (B, N, S, C)
+        ctx.save_for_backward(idx)
+        ctx.mark_non_differentiable(status)
+        return out, status          # status[0] != 0: some index fell outside [0, N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _gstatus):
+        (idx,) = ctx.saved_tensors
+        B, N, S, C = ctx.dims
+        g = _c(g)
+        dp = full((B, N, C), 0.0, g.device)
+        L().scatter_add_rows(g.data_ptr(), idx.data_ptr(), int(idx.dtype == torch.int64), B, N, S, C, dp.data_ptr(),
+                             _stream())
+        return dp, None
 
 
 # =========================================================================================
