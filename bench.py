@@ -403,6 +403,28 @@ def run_gpu(args, real_stdout):
                         "note": "fp32-faithful TF32x3: 3 tcgen05 MMAs per product at half the bf16 rate, so the attainable "
                                 "fraction of the bf16 peak is 1/6 = 0.167",
                         "peak_source": peak_src}
+        if roofline is not None and "note" in roofline:
+            # context for the 1/6 remark: the TF32 tensor-pipe rate of this GPU measured the way MEASURED_PEAKS.json
+            # measures bf16 (cuBLAS matmul 8192^3, best of 10) -- a library call used as a yardstick only
+            try:
+                a_ = torch.randn(8192, 8192, device=dev)
+                b_ = torch.randn(8192, 8192, device=dev)
+                old_tf32 = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = True
+                best = float("inf")
+                for it in range(12):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
+                    if it >= 2:
+                        best = min(best, e0.elapsed_time(e1))
+                torch.backends.cuda.matmul.allow_tf32 = old_tf32
+                tf32_peak = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
+                roofline["tf32_tflops_cublas_live"] = tf32_peak
+                roofline["frac_of_tf32x3_attainable"] = roofline["achieved"] / (tf32_peak / 3.0)
+                del a_, b_
+            except RuntimeError as exc:                          # yardstick only: never fail the bench on it
+                roofline["tf32_tflops_cublas_live"] = None
+                sys.stderr.write("tf32 yardstick skipped: %s\n" % exc)
         if g:
             ach = g[2] / (g[0] / 1e3) / 1e12
             roofline_all = {"kernel": "spgan_gemm, all %d launches of the step" % g[1], "bound": "tensor", "achieved": ach,

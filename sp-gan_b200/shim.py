@@ -9,7 +9,10 @@ What is redirected (module attribute -> replacement):
     Generation.Generator.{Generator, AdaptivePointNorm, EdgeBlock}      Generation/Generator.py:24-261
     Generation.Discriminator.Discriminator                              Generation/Discriminator.py:48-114
     Common.gradient_penalty.GradientPenalty                             Common/gradient_penalty.py:4-37
-    {Generation,Common}.modules.{get_edge_features, edgeConv}           modules.py:683-725, 779-796
+    {Generation,Common}.modules.{get_edge_features, edgeConv, knn, get_graph_feature, pairwise_dist,
+        get_edge_features_xyz}                                          modules.py:629-796
+    Common.ops.{knn, get_graph_feature}, Common.pointnet_util.{square_distance, index_points},
+    Common.pointconv_util.{square_distance, index_points, knn_point}    
         (only patched into those modules if they are imported at all: they pull in heavy, unused code)
 
 `stub_missing=True` registers empty stand-ins for modules the reference imports at start-up but never
@@ -28,9 +31,13 @@ _REDIRECTS = {
     "Generation.Discriminator": ("Discriminator",),
     "Common.gradient_penalty": ("GradientPenalty",),
 }
+_GRAPH = ("knn", "get_graph_feature", "pairwise_dist", "get_edge_features_xyz")        # modules.py:629-680, 727-776
 _PATCH_IF_IMPORTED = {
-    "Generation.modules": ("get_edge_features", "edgeConv"),
-    "Common.modules": ("get_edge_features", "edgeConv"),
+    "Generation.modules": ("get_edge_features", "edgeConv") + _GRAPH,
+    "Common.modules": ("get_edge_features", "edgeConv") + _GRAPH,
+    "Common.ops": ("knn", "get_graph_feature"),                                       # Common/ops.py:129-162
+    "Common.pointnet_util": ("square_distance", "index_points"),                      # pointnet_util.py:19-59
+    "Common.pointconv_util": ("square_distance", "index_points", "knn_point"),        # pointconv_util.py:107-118
 }
 # import-time-only dependencies of Generation/model.py (model.py:16,27; H5DataLoader.py:3; visu_utils.py:16-19;
 # loss_utils.py:12-13,20-21; data_utils.py:8-11)
@@ -113,7 +120,8 @@ def install(stub_missing=False):
         m = sys.modules.get(modname)
         if m is not None:
             for n in names:
-                setattr(m, n, getattr(pkg, n))
+                if hasattr(m, n):                    # Common.modules lacks some of Generation.modules' helpers
+                    setattr(m, n, getattr(pkg, n))
             done.append(modname)
     if stub_missing and not any(isinstance(f, _StubFinder) for f in sys.meta_path):
         sys.meta_path.append(_StubFinder())          # last: only consulted when the real import machinery fails
