@@ -536,6 +536,53 @@ segmax_kernel(const float* __restrict__ x, int C, int64_t seg_rows, float* __res
     }
 }
 
+// float4 variant (C % 4 == 0, 16-byte aligned x): TX column groups of 4 channels x (256 / TX) row lanes per block,
+// so every load is 16 bytes and a warp covers up to 512 contiguous bytes of a row.  Same result as segmax_kernel
+// (max, first arg max) -- the combine below orders by (value desc, row asc).
+template <int TX>
+__global__ void __launch_bounds__(256)
+segmax4_kernel(const float* __restrict__ x, int C4, int64_t seg_rows, float* __restrict__ out,
+               int32_t* __restrict__ arg) {
+    constexpr int TY = 256 / TX;
+    __shared__ float4 bv[TY][TX];
+    __shared__ int4 bi[TY][TX];
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c4 = blockIdx.x * TX + tx;
+    const int64_t seg = blockIdx.y;
+    float best[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int besti[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    if (c4 < C4) {
+        const float4* base = reinterpret_cast<const float4*>(x + seg * seg_rows * (int64_t)C4 * 4) + c4;
+#pragma unroll 4
+        for (int64_t r = ty; r < seg_rows; r += TY) {
+            const float4 v4 = __ldg(base + r * C4);
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (v[q] > best[q] || besti[q] == 0x7fffffff) { best[q] = v[q]; besti[q] = (int)r; }
+        }
+    }
+    bv[ty][tx] = make_float4(best[0], best[1], best[2], best[3]);
+    bi[ty][tx] = make_int4(besti[0], besti[1], besti[2], besti[3]);
+    __syncthreads();
+    if (ty == 0 && c4 < C4) {
+#pragma unroll 1
+        for (int t = 1; t < TY; ++t) {
+            const float4 v4 = bv[t][tx];
+            const int4 j4 = bi[t][tx];
+            const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+            const int j[4] = {j4.x, j4.y, j4.z, j4.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (j[q] != 0x7fffffff && (besti[q] == 0x7fffffff || v[q] > best[q] || (v[q] == best[q] && j[q] < besti[q]))) {
+                    best[q] = v[q]; besti[q] = j[q];
+                }
+        }
+        *reinterpret_cast<float4*>(out + (seg * C4 + c4) * 4) = make_float4(best[0], best[1], best[2], best[3]);
+        if (arg) *reinterpret_cast<int4*>(arg + (seg * C4 + c4) * 4) = make_int4(besti[0], besti[1], besti[2], besti[3]);
+    }
+}
+
 __global__ void segmax_scatter_kernel(const float* __restrict__ g, const int32_t* __restrict__ arg, int64_t nseg,
                                       int C, int64_t seg_rows, float* __restrict__ dx) {
     const int64_t total = nseg * C;
@@ -654,6 +701,7 @@ bn_softmax_mul_k_kernel(const float* __restrict__ xw, const float* __restrict__ 
 }
 // backward of the fused forward up to the two activated tensors: dwa = d/d lrelu(bn(xw)), dya = d/d lrelu(bn(xy));
 // lrelu(bn(xy)) is recomputed from xy.
+template <int KM>
 __global__ void __launch_bounds__(256)
 bn_softmax_mul_k_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xy, const float* __restrict__ w,
                             int64_t P, int k, int C, BnCol by, float slope, float* __restrict__ dwa,
@@ -663,24 +711,32 @@ bn_softmax_mul_k_bwd_kernel(const float* __restrict__ g, const float* __restrict
         const int64_t p = i / C;
         const int c = (int)(i - p * C);
         const int64_t o = p * k * C + c;
-        const float my = __ldg(by.mean + c), ry = __ldg(by.rstd + c), gy = __ldg(by.gamma + c), bby = __ldg(by.beta + c);
-        float gyv[KMAXR], wv[KMAXR];
-        float s = 0.f;
+        // all 3k loads of this (point, channel) are issued before anything depends on them (a store between the
+        // loads of consecutive neighbours serialises them: 3 loads in flight per thread, ~3.7 TB/s)
+        float gv[KM], wv[KM], yv[KM];
 #pragma unroll
-        for (int r = 0; r < KMAXR; ++r)
+        for (int r = 0; r < KM; ++r)
             if (r < k) {
                 const int64_t a = o + (int64_t)r * C;
-                const float gr = __ldg(g + a);
+                gv[r] = __ldg(g + a);
                 wv[r] = __ldg(w + a);
-                gyv[r] = gr * bn_act(__ldg(xy + a), my, ry, gy, bby, slope);
-                s = fmaf(gyv[r], wv[r], s);
-                if (dya) dya[a] = gr * wv[r];
+                yv[r] = __ldg(xy + a);
             }
-        if (dwa) {
+        const float my = __ldg(by.mean + c), ry = __ldg(by.rstd + c), gy = __ldg(by.gamma + c), bby = __ldg(by.beta + c);
+        float s = 0.f;
 #pragma unroll
-            for (int r = 0; r < KMAXR; ++r)
-                if (r < k) dwa[o + (int64_t)r * C] = wv[r] * (gyv[r] - s);
-        }
+        for (int r = 0; r < KM; ++r)
+            if (r < k) {
+                yv[r] = gv[r] * bn_act(yv[r], my, ry, gy, bby, slope);      // g * lrelu(bn(xy))
+                s = fmaf(yv[r], wv[r], s);
+            }
+#pragma unroll
+        for (int r = 0; r < KM; ++r)
+            if (r < k) {
+                const int64_t a = o + (int64_t)r * C;
+                if (dya) dya[a] = gv[r] * wv[r];
+                if (dwa) dwa[a] = wv[r] * (yv[r] - s);
+            }
     }
 }
 __global__ void softmax_mul_k_bwd_kernel(const float* __restrict__ g, const float* __restrict__ yv,
@@ -1027,6 +1083,14 @@ extern "C" int spgan_segmax(const float* x, int64_t R, int C, int64_t seg_rows, 
     if (R == 0) return SPGAN_OK;
     const int64_t nseg = R / seg_rows;
     if (nseg > 65535) return SPGAN_E_UNSUPPORTED;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                        reinterpret_cast<uintptr_t>(arg)) & 15) == 0;
+    if (C % 4 == 0 && al16) {
+        const int C4 = C / 4;
+        if (C4 >= 64) segmax4_kernel<32><<<dim3((C4 + 31) / 32, (unsigned)nseg), 256, 0, as_stream(s)>>>(x, C4, seg_rows, out, arg);
+        else segmax4_kernel<8><<<dim3((C4 + 7) / 8, (unsigned)nseg), 256, 0, as_stream(s)>>>(x, C4, seg_rows, out, arg);
+        return spgan_launch_status();
+    }
     dim3 grid((C + 31) / 32, (unsigned)nseg), block(32, 8);
     segmax_kernel<<<grid, block, 0, as_stream(s)>>>(x, C, seg_rows, out, arg);
     return spgan_launch_status();
@@ -1097,8 +1161,11 @@ extern "C" int spgan_bn_softmax_mul_k_bwd(const float* g, const float* xy, const
     SPGAN_CHECK_ARG(g && xy && w && mean_y && rstd_y && gamma_y && beta_y && P >= 0 && k >= 1 && C >= 1);
     if (k > KMAXR) return SPGAN_E_UNSUPPORTED;
     if (P == 0) return SPGAN_OK;
-    bn_softmax_mul_k_bwd_kernel<<<ew_grid(P * C, 256, 16), 256, 0, as_stream(s)>>>(
-        g, xy, w, P, k, C, BnCol{mean_y, rstd_y, gamma_y, beta_y}, slope, dwa, dya);
+    const BnCol cy{mean_y, rstd_y, gamma_y, beta_y};
+    if (k <= 10)
+        bn_softmax_mul_k_bwd_kernel<10><<<ew_grid(P * C, 256, 32), 256, 0, as_stream(s)>>>(g, xy, w, P, k, C, cy, slope, dwa, dya);
+    else
+        bn_softmax_mul_k_bwd_kernel<KMAXR><<<ew_grid(P * C, 256, 32), 256, 0, as_stream(s)>>>(g, xy, w, P, k, C, cy, slope, dwa, dya);
     return spgan_launch_status();
 }
 extern "C" int spgan_kmax(const float* x, int64_t P, int k, int C, float* out, int32_t* arg, spgan_stream_t s) {
