@@ -61,16 +61,19 @@ colreduce_partial_kernel(Op op, int C, int64_t seg_rows, int chunks, int64_t row
     }
 }
 
-constexpr int FIN_TY = 16;                // chunk lanes of the finalize block
+constexpr int FIN_TX = 8;                 // columns per finalize block
+constexpr int FIN_TY = 64;                // chunk lanes of the finalize block
 template <int NV, typename Fin>
-__global__ void __launch_bounds__(32 * FIN_TY)
+__global__ void __launch_bounds__(FIN_TX * FIN_TY)
 colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, int chunks, Fin fin) {
-    // block = 32 columns x 16 chunk lanes of one segment: every partial row is read as one coalesced 128-byte
-    // line per warp, 8 independent loads in flight per thread (a narrow tensor has up to ~1200 chunk rows and only
-    // C / 32 blocks: the pass is latency-bound); double-precision combine in a fixed order => deterministic
-    __shared__ double red[FIN_TY][NV][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + tx;
+    // block = 8 columns x 64 chunk lanes of one segment.  A narrow tensor has up to ~1200 chunk rows and few
+    // columns, so the pass is latency-bound: narrow column groups give C / 8 blocks (a 32-column block left a C = 64
+    // BatchNorm with 2 blocks walking 73 dependent batches), every thread keeps 8 independent loads in flight, and
+    // each partial row is read as one 32-byte sector per group.  Double-precision combine in a fixed order =>
+    // deterministic.
+    __shared__ double red[FIN_TY][NV][FIN_TX + 1];
+    const int tx = threadIdx.x % FIN_TX, ty = threadIdx.x / FIN_TX;
+    const int c = blockIdx.x * FIN_TX + tx;
     for (int64_t seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
         double s[NV];
 #pragma unroll
@@ -89,19 +92,44 @@ colreduce_final_kernel(const float* __restrict__ partial, int C, int64_t nseg, i
 #pragma unroll
                     for (int v = 0; v < NV; ++v) s[v] += (double)t[q][v];
             }
-            for (; ch < chunks; ch += FIN_TY)
+            {   // tail: up to 7 more rows per lane, again all loads first
+                float t[7][NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) s[v] += (double)__ldg(base + ((int64_t)ch * NV + v) * C);
+                for (int q = 0; q < 7; ++q)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        t[q][v] = (ch + q * FIN_TY < chunks) ? __ldg(base + ((int64_t)(ch + q * FIN_TY) * NV + v) * C) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 7; ++q)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) s[v] += (double)t[q][v];
+            }
         }
 #pragma unroll
         for (int v = 0; v < NV; ++v) red[ty][v][tx] = s[v];
+        __syncthreads();
+        // two fixed-order levels: lanes ty < 8 fold rows ty*8 .. ty*8+7, lane 0 folds the 8 results
+        if (ty < 8) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                double t = red[ty * 8][v][tx];
+#pragma unroll
+                for (int y = 1; y < 8; ++y) t += red[ty * 8 + y][v][tx];
+                s[v] = t;
+            }
+        }
+        __syncthreads();
+        if (ty < 8) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) red[ty][v][tx] = s[v];
+        }
         __syncthreads();
         if (ty == 0 && c < C) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 double t = red[0][v][tx];
 #pragma unroll
-                for (int y = 1; y < FIN_TY; ++y) t += red[y][v][tx];
+                for (int y = 1; y < 8; ++y) t += red[y][v][tx];
                 s[v] = t;
             }
             fin(seg, c, s);
@@ -160,7 +188,7 @@ int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStrea
     if (chunks <= 8)
         colreduce_final_small_kernel<NV><<<ew_grid(nseg * C, 256), 256, 0, st>>>(partial, C, nseg, chunks, fin);
     else
-        colreduce_final_kernel<NV><<<dim3((unsigned)((C + 31) / 32), (unsigned)(nseg < 4096 ? nseg : 4096)), 32 * FIN_TY, 0, st>>>(partial, C, nseg, chunks, fin);
+        colreduce_final_kernel<NV><<<dim3((unsigned)((C + FIN_TX - 1) / FIN_TX), (unsigned)(nseg < 4096 ? nseg : 4096)), FIN_TX * FIN_TY, 0, st>>>(partial, C, nseg, chunks, fin);
     return spgan_launch_status();
 }
 
@@ -243,12 +271,14 @@ using fastnorm::ld4; using fastnorm::st4; using fastnorm::f4; using fastnorm::ad
 using fastnorm::mul4; using fastnorm::fma4; using fastnorm::mask4; using fastnorm::lrelu4;
 struct NoState {};
 struct SumOp4 {
+    static constexpr int kStreams = 1;      // input tensors read per row (sets the unroll depth)
     const float* x; int C;
     using State = NoState;
     __device__ State init(int, int64_t) const { return State{}; }
     __device__ void accum(const State&, int64_t r, int c4, float4* acc) const { acc[0] = add4(acc[0], ld4(x + r * C + c4 * 4)); }
 };
 struct DotOp4 {
+    static constexpr int kStreams = 2;      // input tensors read per row (sets the unroll depth)
     const float* x; const float* y; int C;
     using State = NoState;
     __device__ State init(int, int64_t) const { return State{}; }
@@ -257,6 +287,7 @@ struct DotOp4 {
     }
 };
 struct StatsOp4 {
+    static constexpr int kStreams = 1;      // input tensors read per row (sets the unroll depth)
     const float* x; int C; int64_t seg_rows;
     struct State { float4 shift; };
     __device__ State init(int c4, int64_t seg) const { return State{ld4(x + seg * seg_rows * C + c4 * 4)}; }
@@ -266,6 +297,7 @@ struct StatsOp4 {
     }
 };
 struct NormBwdOp4 {
+    static constexpr int kStreams = 2;      // input tensors read per row (sets the unroll depth)
     const float* g; const float* x; float slope; int C; const float* mean; const float* rstd;
     const float* gamma; const float* beta;
     struct State { float4 mean, rstd, gamma, beta; };
@@ -282,6 +314,7 @@ struct NormBwdOp4 {
     }
 };
 struct DblBwdOp4 {
+    static constexpr int kStreams = 3;      // input tensors read per row (sets the unroll depth)
     const float* g; const float* u; const float* x; int C; const float* mean;
     struct State { float4 mean; };
     __device__ State init(int c4, int64_t) const { return State{ld4(mean + c4 * 4)}; }
@@ -358,6 +391,7 @@ struct DblBwdApplyOp4 {
 // pre-activation is <= 0) is piecewise constant in x, so the closed form of plain BatchNorm applies to
 // g' = m * g, and the cotangent reaching g is m * gg'.  The mask is recomputed from x on the fly.
 struct DblBwdActOp4 {
+    static constexpr int kStreams = 3;      // input tensors read per row (sets the unroll depth)
     const float* g; const float* u; const float* x; float slope; int C; const float* mean; const float* rstd;
     const float* gamma; const float* beta;
     struct State { float4 mean, rstd, gamma, beta; };
