@@ -1,6 +1,7 @@
 // Column reductions, batch/instance normalisation (forward, backward, double backward),
 // poolings over points / neighbours, softmax over neighbours, edge aggregation, penalty.
 #include "common.cuh"
+#include <stdlib.h>
 #include "norm_fast.cuh"
 #include <float.h>
 
@@ -157,7 +158,15 @@ __global__ void colreduce_final_small_kernel(const float* __restrict__ partial, 
 
 // (measured: 24 * 148 blocks is much slower -- chunks of a few dozen rows make the per-block reduction and the
 // finalize pass dominate; 8 * 148 stays)
-constexpr int kReduceTargetBlocks = 8 * kNumSMs;
+inline int reduce_target_blocks() {       // SPGAN_REDUCE_WAVES = CTAs per SM the partial pass aims for (tuning knob)
+    static const int v = [] {
+        const char* e = getenv("SPGAN_REDUCE_WAVES");
+        const int w = e ? atoi(e) : 0;
+        return (w >= 1 && w <= 32 ? w : 8) * kNumSMs;
+    }();
+    return v;
+}
+#define kReduceTargetBlocks reduce_target_blocks()
 
 template <int NV, typename Op, typename Op4, typename Fin>
 int run_colreduce(int64_t R, int C, int64_t seg_rows, void* workspace, cudaStream_t st, Op op, Op4 op4, bool can_vec,
