@@ -381,7 +381,26 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                     *reinterpret_cast<float4*>(T + lane * EPI_LD + 4 * (q ^ (lane & 7))) =
                         make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 __syncwarp();
-                if (n0 + c0 < N) {
+                if (vecC && m0 + 32 <= M && n0 + c0 + 32 <= N) {
+                    // interior chunk (every chunk of the step's shapes): no per-element bounds tests or index
+                    // arithmetic -- one pointer walking 4 rows per step.  (The guarded loop below costs ~580 warp
+                    // instructions per 32 x 32 chunk and made the epilogue warps the pace of every K <= 128 GEMM.)
+                    const int g = lane & 7;
+                    float* cp = C + (m0 + (lane >> 3)) * ldc + colv;
+                    const int64_t step = 4 * ldc;
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = rr * 4 + (lane >> 3);
+                        float4 o = *reinterpret_cast<const float4*>(T + r * EPI_LD + 4 * (g ^ (r & 7)));
+                        if (bias_v) { o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+                        if (accumulate) {
+                            const float4 old = *reinterpret_cast<const float4*>(cp);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(cp) = o;
+                        cp += step;
+                    }
+                } else if (n0 + c0 < N) {
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
                         const int r = rr * 4 + (lane >> 3), g = lane & 7, cq = g * 4;
