@@ -105,6 +105,19 @@ int spgan_gather_rows(const float *points, const void *idx, int idx_is_int64, in
 int spgan_scatter_add_rows(const float *g, const void *idx, int idx_is_int64, int B, int N, int64_t S, int C,
                            float *dpoints, spgan_stream_t stream);
 
+/* ------------------------------------------------------------------ approximate EMD
+ * The synchronous auction of metrics/emd/emd_cuda.cu:95-282 behind emdModule (metrics/emd/emd_module.py:33-71;
+ * called with eps 0.005, 300 iterations at Common/GAN_metrics.py:375-379, 406-407): xyz1, xyz2 [B,n,3] ->
+ * dist [B,n] (squared distance of every point of xyz1 to its matched point of xyz2) and assignment [B,n].
+ * One CTA per cloud pair runs all iterations out of shared memory: no global scratch (the reference passes nine
+ * work arrays), n <= ~5200, n need not be a multiple of 1024, iters >= 1.  Arithmetic and tie rules:
+ * oracle/emd_recipe.c (bit-identical results).  spgan_emd_grad: gxyz1 = 2 graddist (xyz1 - xyz2[assignment])
+ * (emd_cuda.cu:283-316; the reference computes no gradient for xyz2 either). */
+int spgan_emd_auction(const float *xyz1, const float *xyz2, int B, int n, float eps, int iters, float *dist,
+                      int32_t *assignment, spgan_stream_t stream);
+int spgan_emd_grad(const float *xyz1, const float *xyz2, const float *graddist, const int32_t *assignment, int B,
+                   int n, float *gxyz1, spgan_stream_t stream);
+
 /* ------------------------------------------------------------------ layout
  * [B,C,N] (arbitrary element strides sb, sc, sn) <-> point-major rows [B*N, C].
  * Replaces the transpose/contiguous calls of Generator.py:167,170 and the strided read of

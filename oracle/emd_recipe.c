@@ -1,0 +1,117 @@
+/*
+ * oracle/emd_recipe.c -- TEST INFRASTRUCTURE ONLY (never imported by the product path).
+ *
+ * Sequential C restatement of the approximate Earth Mover's Distance the reference evaluates with
+ * (SURVEY 8f-2): the synchronous auction of metrics/emd/emd_cuda.cu:95-215 (MSN, Liu et al. AAAI'20), called as
+ * emdModule()(sample, ref, 0.005, 300) at Common/GAN_metrics.py:375-379, 406-407.
+ *
+ * PARITY UNPINNED: the reference holds no CPU implementation, test or golden vector for this path, its CUDA
+ * extension cannot be built or run in the build container (torch extension, no GPU), and `match_cost`, which
+ * metrics/evaluation_metrics.py:8-10 imports for the EMD half of the evaluation, is un-vendored (PointFlow
+ * StructuralLosses, no version pinned).  This file restates the published algorithm as emd_cuda.cu executes it,
+ * one iteration = Bid (:95-178), GetMax (:180-193), Assign (:195-215), then CalcDist (:217-226), with the two
+ * choices the CUDA source leaves to the hardware made explicit:
+ *   - squared distances are formed as fma(z,z, fma(y,y, x*x)) (what nvcc's default -fmad=true emits for
+ *     x*x + y*y + z*z), sqrtf is correctly rounded, and `3.0 - sqrtf(.) - price` is evaluated in double and
+ *     rounded once (the literal 3.0 is a double in the source, :142);
+ *   - when several unassigned points bid the same increment (within the source's 1e-6 window, :187) for one
+ *     target, the source lets the last writer of max_idx win (a race); here the HIGHEST point index wins.
+ * Everything else (strict '>' scans in ascending target order, top-2 merge, eviction, price update, the
+ * "assign every leftover to its bid" last iteration, :201) follows the source exactly.
+ *
+ * Build: gcc -O2 -fPIC -shared -ffp-contract=off -march=x86-64-v3 (only the explicit fmaf() may fuse).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+/* xyz1, xyz2: [n, 3]; dist: [n]; assignment: [n] int32.  Returns 0, -1 on bad arguments. */
+static int emd_one(const float *xyz1, const float *xyz2, int n, float eps, int iters, float *dist,
+                   int32_t *assignment, int32_t *n_unassigned_trace) {
+    if (n < 1 || iters < 1) return -1;
+    int32_t *ass_inv = (int32_t *)malloc(sizeof(int32_t) * n), *bid = (int32_t *)malloc(sizeof(int32_t) * n);
+    int32_t *max_idx = (int32_t *)malloc(sizeof(int32_t) * n), *unass = (int32_t *)malloc(sizeof(int32_t) * n);
+    float *price = (float *)malloc(sizeof(float) * n), *bid_inc = (float *)malloc(sizeof(float) * n);
+    float *max_inc = (float *)malloc(sizeof(float) * n);
+    for (int j = 0; j < n; ++j) {
+        assignment[j] = -1; ass_inv[j] = -1; bid[j] = 0; max_idx[j] = 0;       /* emd_module.py:45-52 */
+        price[j] = 0.f; bid_inc[j] = 0.f; max_inc[j] = 0.f;
+    }
+    for (int it = 0; it < iters; ++it) {
+        const int last = (it == iters - 1);
+        int nu = 0;
+        for (int j = 0; j < n; ++j)
+            if (assignment[j] == -1) unass[nu++] = j;          /* the set every phase of this iteration sees */
+        if (n_unassigned_trace) n_unassigned_trace[it] = nu;
+        /* ---- Bid (emd_cuda.cu:95-178) */
+        for (int u = 0; u < nu; ++u) {
+            const int j = unass[u];
+            const float x1 = xyz1[j * 3 + 0], y1 = xyz1[j * 3 + 1], z1 = xyz1[j * 3 + 2];
+            float best = -1e9f, better = -1e9f;
+            int best_i = -1;
+            for (int k = 0; k < n; ++k) {
+                const float x2 = xyz2[k * 3 + 0] - x1, y2 = xyz2[k * 3 + 1] - y1, z2 = xyz2[k * 3 + 2] - z1;
+                const float sq = fmaf(z2, z2, fmaf(y2, y2, x2 * x2));
+                const float d = (float)(3.0 - (double)sqrtf(sq) - (double)price[k]);
+                if (d > best) { better = best; best = d; best_i = k; }
+                else if (d > better) better = d;
+            }
+            const float inc = (best - better) + eps;
+            bid[j] = best_i;
+            bid_inc[j] = inc;
+            if (inc > max_inc[best_i]) max_inc[best_i] = inc;                  /* atomicMax, :176 */
+        }
+        /* ---- GetMax (:180-193); ascending j => the highest eligible index wins */
+        for (int u = 0; u < nu; ++u) {
+            const int j = unass[u];
+            const double bi = (double)bid_inc[j], mi = (double)max_inc[bid[j]];
+            if (bi - 1e-6 <= mi && mi <= bi + 1e-6) max_idx[bid[j]] = j;
+        }
+        /* ---- Assign (:195-215) */
+        for (int u = 0; u < nu; ++u) {
+            const int j = unass[u];
+            const int t = bid[j];
+            if (last || max_idx[t] == j) {
+                const int prev = ass_inv[t];
+                if (!last && prev != -1) assignment[prev] = -1;
+                ass_inv[t] = j;
+                assignment[j] = t;
+                price[t] += bid_inc[j];
+                max_inc[t] = -1e9f;
+            }
+        }
+    }
+    /* ---- CalcDist (:217-226) */
+    for (int j = 0; j < n; ++j) {
+        const int k = assignment[j];
+        const float dx = xyz1[j * 3 + 0] - xyz2[k * 3 + 0], dy = xyz1[j * 3 + 1] - xyz2[k * 3 + 1],
+                    dz = xyz1[j * 3 + 2] - xyz2[k * 3 + 2];
+        dist[j] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    }
+    free(ass_inv); free(bid); free(max_idx); free(unass); free(price); free(bid_inc); free(max_inc);
+    return 0;
+}
+
+/* xyz1, xyz2: [B, n, 3]; dist [B, n]; assignment [B, n].  trace (optional): [B, iters] unassigned counts. */
+int spgan_oracle_emd(const float *xyz1, const float *xyz2, int B, int n, float eps, int iters, float *dist,
+                     int32_t *assignment, int32_t *trace) {
+    if (B < 0) return -1;
+    for (int b = 0; b < B; ++b) {
+        const int rc = emd_one(xyz1 + (int64_t)b * n * 3, xyz2 + (int64_t)b * n * 3, n, eps, iters,
+                               dist + (int64_t)b * n, assignment + (int64_t)b * n,
+                               trace ? trace + (int64_t)b * iters : NULL);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* d xyz1 of sum_j g[j] * dist[j] (NmDistanceGradKernel, :283-300): 2 g (p1 - p2[assignment]). */
+void spgan_oracle_emd_grad(const float *xyz1, const float *xyz2, const float *g, const int32_t *assignment, int B,
+                           int n, float *gxyz1) {
+    for (int64_t i = 0; i < (int64_t)B * n; ++i) {
+        const int64_t b = i / n;
+        const int64_t k = b * n + assignment[i];
+        const float gg = g[i] * 2.f;
+        for (int c = 0; c < 3; ++c) gxyz1[i * 3 + c] = gg * (xyz1[i * 3 + c] - xyz2[k * 3 + c]);
+    }
+}

@@ -9,6 +9,7 @@ What is redirected (module attribute -> replacement):
     Generation.Generator.{Generator, AdaptivePointNorm, EdgeBlock}      Generation/Generator.py:24-261
     Generation.Discriminator.Discriminator                              Generation/Discriminator.py:48-114
     Common.gradient_penalty.GradientPenalty                             Common/gradient_penalty.py:4-37
+    CD_EMD.emd_.emd_module / metrics.emd.emd_module .{emdModule, emdFunction}   metrics/emd/emd_module.py:33-71
     {Generation,Common}.modules.{get_edge_features, edgeConv, knn, get_graph_feature, pairwise_dist,
         get_edge_features_xyz}                                          modules.py:629-796
     Common.ops.{knn, get_graph_feature}, Common.pointnet_util.{square_distance, index_points},
@@ -30,6 +31,14 @@ _REDIRECTS = {
     "Generation.Generator": ("Generator", "AdaptivePointNorm", "EdgeBlock"),
     "Generation.Discriminator": ("Discriminator",),
     "Common.gradient_penalty": ("GradientPenalty",),
+    # `from CD_EMD.emd_ import emd_module` (GAN_metrics.py:15, loss_utils.py:20, data_utils.py:10) and
+    # `metrics/emd/emd_module.py`: emdModule / emdFunction over the auction kernel
+    "CD_EMD.emd_.emd_module": ("emdModule", "emdFunction"),
+}
+# redirected only when the parent package really is on sys.path (a generic name like `metrics` must not be shadowed
+# by an empty stand-in): metrics/emd/emd_module.py:33-71
+_REDIRECT_IF_PARENT = {
+    "metrics.emd.emd_module": ("emdModule", "emdFunction"),
 }
 _GRAPH = ("knn", "get_graph_feature", "pairwise_dist", "get_edge_features_xyz")        # modules.py:629-680, 727-776
 _PATCH_IF_IMPORTED = {
@@ -104,7 +113,14 @@ def install(stub_missing=False):
     """Idempotent.  Returns the list of module names that were (re)directed."""
     import spgan_b200 as pkg
     done = []
-    for modname, names in _REDIRECTS.items():
+    redirects = dict(_REDIRECTS)
+    for modname, names in _REDIRECT_IF_PARENT.items():
+        try:
+            if importlib.util.find_spec(modname.rsplit(".", 1)[0]) is not None:
+                redirects[modname] = names
+        except (ImportError, ValueError, AttributeError):
+            pass
+    for modname, names in redirects.items():
         _ensure_parent(modname)
         m = types.ModuleType(modname)
         m.__doc__ = "spgan_b200 drop-in for %s" % modname
@@ -130,7 +146,7 @@ def install(stub_missing=False):
 
 
 def uninstall():
-    for modname in _REDIRECTS:
+    for modname in list(_REDIRECTS) + list(_REDIRECT_IF_PARENT):
         m = sys.modules.get(modname)
         if m is not None and getattr(m, "__spgan_b200__", False):
             del sys.modules[modname]

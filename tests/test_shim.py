@@ -25,8 +25,11 @@ def test_shim_redirects_without_reference_tree():
              "from Common.gradient_penalty import GradientPenalty\n"
              "assert Generator is spgan_b200.Generator and Discriminator is spgan_b200.Discriminator\n"
              "assert GradientPenalty is spgan_b200.GradientPenalty and EdgeBlock is spgan_b200.EdgeBlock\n"
+             "from CD_EMD.emd_ import emd_module\n"                      # GAN_metrics.py:15, loss_utils.py:20
+             "assert emd_module.emdModule is spgan_b200.emdModule\n"
+             "import sys; assert 'metrics' not in sys.modules\n"          # generic names are never shadowed
              "shim.uninstall()\n"
-             "import sys; assert 'Generation.Generator' not in sys.modules\n"
+             "assert 'Generation.Generator' not in sys.modules and 'CD_EMD.emd_.emd_module' not in sys.modules\n"
              "print('ok')")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
