@@ -306,14 +306,14 @@ def run_gpu(args, real_stdout):
             byshape = {}
             for name, ia, s_, e_ in prof:
                 if name == "spgan_gemm":
-                    key = ("T" if ia[0] else "N") + ("T" if ia[1] else "N") + " M=%d N=%d K=%d" % (ia[2], ia[3], ia[4])
+                    key = (bool(ia[0]), bool(ia[1]), ia[2], ia[3], ia[4])              # transA, transB, M, N, K
                     b = byshape.setdefault(key, [0.0, 0])
                     b[0] += s_.elapsed_time(e_)
                     b[1] += 1
-            for key, b in sorted(byshape.items(), key=lambda kv: -kv[1][0])[:25]:
+            for (ta, tb, M_, N_, K_), b in sorted(byshape.items(), key=lambda kv: -kv[1][0])[:25]:
+                label = ("T" if ta else "N") + ("T" if tb else "N") + " M=%d N=%d K=%d" % (M_, N_, K_)
                 sys.stderr.write("%-40s x%-3d %8.3f ms  %6.1f TFLOP/s\n" % (
-                    key, b[1], b[0], 2.0 * eval(key.split("M=")[1].split()[0]) * eval(key.split("N=")[1].split()[0]) *
-                    eval(key.split("K=")[1]) * b[1] / b[0] / 1e9))
+                    label, b[1], b[0], 2.0 * M_ * N_ * K_ * b[1] / b[0] / 1e9))
         if os.environ.get("SPGAN_BENCH_BW_TABLE") == "1":          # diagnostic: HBM-bound entry points (stderr)
             # algorithmic bytes per call from the integer arguments (R or P, C, k ...) of each C-ABI call
             def nbytes(name, ia):
