@@ -285,6 +285,8 @@ int spgan_gemm_simt(int transA, int transB, int64_t M, int N, int K, const float
 
 size_t spgan_gemm_tc_workspace(int N, int K);
 bool spgan_gemm_tc_supported(int transA, int64_t M, int N, int K);
+int spgan_gemm_tc_f16s(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                       float* C, int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st);
 int spgan_gemm_tc(int mode_bf16, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
                   int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, void* workspace,
                   cudaStream_t st);
@@ -302,7 +304,7 @@ extern "C" size_t spgan_gemm_workspace(int engine, int N, int K) {
     if (N < 1 || K < 1) return 0;
     // deterministic split-K partial tiles of the small-batch path (any engine)
     const size_t small_m = (K >= 256 && K < 2048) ? (size_t)kSmallMSplits * kSmallMRows * N * sizeof(float) : 0;
-    const size_t tc = (engine == 1 || engine == 2) ? spgan_gemm_tc_workspace(N, K) : 0;
+    const size_t tc = (engine >= 1 && engine <= 3) ? spgan_gemm_tc_workspace(N, K) : 0;
     return small_m > tc ? small_m : tc;
 }
 
@@ -312,6 +314,12 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
     SPGAN_CHECK_ARG(A && B && C && M >= 0 && N >= 1 && K >= 1);
     SPGAN_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N);
     if (M == 0) return SPGAN_OK;
+    // engine 3 (opt-in): fp16x3 with scaled residuals for the forward / dgrad products (gemm_tc_f16s.cu); weight
+    // gradients and everything the tensor path does not take fall through to engine 1's routes below
+    if (engine == 3 && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
+        workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
+        return spgan_gemm_tc_f16s(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, as_stream(stream));
+    if (engine == 3) engine = 1;
     if ((engine == 1 || engine == 2) && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
         workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
         return spgan_gemm_tc(engine == 2, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,

@@ -32,7 +32,7 @@ _INPUT_GRAD_ONLY = False
 
 # engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores with the fp32-faithful TF32x3
 # split wherever the shape allows (default), 2 = tcgen05 with the faster bf16x3 split (~2^-16/product).
-# Override with SPGAN_GEMM_ENGINE.
+# Override with SPGAN_GEMM_ENGINE.  3 = opt-in fp16x3 with scaled residuals (csrc/gemm_tc_f16s.cu, not yet validated).
 import os as _os
 GEMM_ENGINE = int(_os.environ.get("SPGAN_GEMM_ENGINE", "1"))
 
@@ -153,7 +153,7 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
         bias = _c(bias)
     engine = GEMM_ENGINE if engine is None else engine
     ws, ws_bytes = None, 0
-    tc = engine in (1, 2) and ((not ta and M >= 128 and N >= 16 and K >= 16) or
+    tc = engine in (1, 2, 3) and ((not ta and M >= 128 and N >= 16 and K >= 16) or
                                (ta and not tb and bias is None and K >= 4096 and M >= 16 and N >= 16))
     if tc or (M <= 128 and 256 <= K < 2048):         # tensor-core operands / small-batch split-K partial tiles
         ws_bytes = L().gemm_workspace(engine, N, K)
