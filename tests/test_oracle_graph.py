@@ -60,3 +60,28 @@ def test_get_edge_features_xyz():
     g = golden("graph_util")
     fea, xyz = P.get_edge_features_xyz(g["efx_x"], g["efx_pc"], int(g["efx_k"]))
     assert np.array_equal(fea, g["efx_fea"]) and np.array_equal(xyz, g["efx_xyz"])
+
+
+# ---- the same restatements against torch CPU itself on fresh random shapes (not only the stored goldens)
+@pytest.mark.parametrize("B,C,N", [(1, 3, 64), (2, 6, 33), (1, 64, 96), (2, 17, 100), (1, 128, 40)])
+def test_knn_distance_matches_torch_cpu_bitwise(B, C, N):
+    import torch
+    x = torch.randn(B, C, N, generator=torch.Generator().manual_seed(B * 100 + C + N))
+    inner = -2 * torch.matmul(x.transpose(2, 1), x)                  # Generation/modules.py:641-643
+    xx = torch.sum(x ** 2, dim=1, keepdim=True)
+    pd = -xx - inner - xx.transpose(2, 1)
+    assert np.array_equal(-P.knn_dist(x.numpy()), pd.numpy())
+    k = min(5, N)
+    ref = pd.topk(k=k, dim=-1)[1].numpy()
+    assert same_topk(-pd.numpy(), P.knn(x.numpy(), k), ref, ordered=True)
+
+
+@pytest.mark.parametrize("B,N,M", [(1, 50, 70), (2, 33, 33), (1, 128, 5)])
+def test_square_distance_xyz_matches_torch_cpu_bitwise(B, N, M):
+    import torch
+    g = torch.Generator().manual_seed(N * 7 + M)
+    src, dst = torch.randn(B, N, 3, generator=g), torch.randn(B, M, 3, generator=g)
+    dist = -2 * torch.matmul(src, dst.permute(0, 2, 1))             # Common/pointnet_util.py:36-39
+    dist += torch.sum(src ** 2, -1).view(B, N, 1)
+    dist += torch.sum(dst ** 2, -1).view(B, 1, M)
+    assert np.array_equal(P.square_distance(src.numpy(), dst.numpy()), dist.numpy())
