@@ -18,6 +18,11 @@
  *     cudaError_t if the launch failed.  Nothing ever calls exit() or prints.
  *   - "rows" matrices are row-major fp32 [R, C] with an explicit leading dimension where
  *     noted; the reference's channel-first tensors are [B, C, N].
+ *   - tuning knobs: a few entry points read an environment variable ONCE per process (never afterwards, so
+ *     the library stays free of mutable state): SPGAN_TC_PF = 2|3|4 (A-operand prefetch ring of the tcgen05
+ *     GEMM), SPGAN_TC_FENCE = producer|consumer (where its proxy fence runs), SPGAN_REDUCE_WAVES = 1..32
+ *     (CTAs per SM of the column reductions), SPGAN_KNN_WS = 1 (opt-in warp-specialised kNN kernel, same
+ *     results).  Defaults are the measured best; none changes a result except through fp32 summation order.
  */
 #ifndef SPGAN_B200_H_
 #define SPGAN_B200_H_
