@@ -14,11 +14,11 @@ from .pointnet_util import (knn, get_graph_feature, pairwise_dist, square_distan
                             index_points, get_edge_features_xyz)
 from . import emd  # noqa: F401
 from .emd import emdModule, emdFunction, emd_approx  # noqa: F401
-from .metrics import pairwise_CD, lgan_mmd_cov, one_nn_accuracy  # noqa: F401
+from .metrics import pairwise_CD, pairwise_EMD, lgan_mmd_cov, one_nn_accuracy  # noqa: F401
 from .train_step import WGANGPTrainer, dis_loss_wgan, gen_loss_wgan, requires_grad  # noqa: F401
 
 __all__ = ["ops", "get_edge_features", "edgeConv", "EdgeBlock", "Generator", "AdaptivePointNorm",
            "Discriminator", "GradientPenalty", "WGANGPTrainer", "dis_loss_wgan", "gen_loss_wgan",
-           "requires_grad", "pairwise_CD", "lgan_mmd_cov", "one_nn_accuracy", "pointnet_util", "knn",
+           "requires_grad", "pairwise_CD", "pairwise_EMD", "lgan_mmd_cov", "one_nn_accuracy", "pointnet_util", "knn",
            "get_graph_feature", "pairwise_dist", "square_distance", "knn_point", "index_points",
            "get_edge_features_xyz", "emd", "emdModule", "emdFunction", "emd_approx"]

@@ -36,6 +36,40 @@ def pairwise_CD(sample_pcs, ref_pcs, batch_size=None, shard=True):
     return full[:S]
 
 
+def pairwise_EMD(sample_pcs, ref_pcs, batch_size=None, eps=0.005, iters=300, shard=True):
+    """The EMD half of `_pairwise_EMD_CD_` (metrics/evaluation_metrics.py:89-125): sample_pcs [S, N, 3], ref_pcs
+    [R, N, 3] -> all_emd [S, R] with all_emd[i, j] = mean over the points of sample_i of the matched L2 distance to
+    ref_j (what `emd_approx` = match_cost / N returns per pair, :28-36; here the matching is the auction of
+    spgan_b200.emd with the reference's eps / iteration count, GAN_metrics.py:406-407).  Rows are sharded over the
+    ranks of an initialised process group like pairwise_CD.  `batch_size` bounds the reference clouds per launch
+    (default: all R; each launch expands one sample cloud R-fold like the reference's own loop).
+    Round-1 status: composed from validated kernels, itself exercised only by the opt-in test
+    (SPGAN_TEST_PAIRWISE_EMD=1 pytest tests/test_gpu_chamfer.py)."""
+    from .emd import emdFunction
+    a, b = ops._c(sample_pcs), ops._c(ref_pcs)
+    S, N, _ = a.shape
+    R = b.shape[0]
+    if b.shape[1] != N:
+        raise AssertionError("pairwise_EMD: clouds must have the same number of points")
+    world = dist.get_world_size() if (shard and dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    rows = (S + world - 1) // world
+    i0, i1 = min(S, rank * rows), min(S, (rank + 1) * rows)
+    part = torch.zeros((rows if world > 1 else S, R), device=a.device, dtype=torch.float32)
+    bs = R if not batch_size else int(batch_size)
+    with torch.no_grad():
+        for i in range(i0, i1):
+            for r0 in range(0, R, bs):
+                rb = b[r0:r0 + bs]
+                d, _ = emdFunction.apply(a[i:i + 1].expand(rb.shape[0], N, 3), rb, eps, iters)
+                part[i - i0, r0:r0 + rb.shape[0]] = d.sqrt().mean(dim=1)      # O(R*N) post-processing of the result
+    if world == 1:
+        return part
+    full = torch.empty((world * rows, R), device=a.device, dtype=torch.float32)
+    dist.all_gather_into_tensor(full, part)
+    return full[:S]
+
+
 def dist_chamfer(a, b):
     """distChamfer-style per-pair call (evaluation_metrics.py:37-49) for equal-length batches:
     a [B, N, 3], b [B, M, 3] -> (mean_m-side, mean_n-side) directed means are not what the reference returns

@@ -63,3 +63,20 @@ def test_pairwise_cd_on_synthetic_chairs_full_size():
     b = R.synthetic_chairs(rng, 2, 2048)
     cd = pkg.pairwise_CD(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
     assert_rel(cd, C.pairwise_cd_exact(a, b), 2e-5, "chairs 2048")
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SPGAN_TEST_PAIRWISE_EMD") != "1",
+                    reason="pairwise_EMD is composed from validated kernels but has not itself run on a GPU yet")
+def test_pairwise_emd_matches_oracle():
+    """all_emd[i, j] = mean_j sqrt(dist) of the auction between sample_i and ref_j (evaluation_metrics.py:89-125)."""
+    import spgan_b200 as pkg
+    from oracle import emd_ref
+    rng = np.random.default_rng(5)
+    smp = rng.random((3, 128, 3), dtype=np.float32)
+    ref = rng.random((4, 128, 3), dtype=np.float32)
+    out = pkg.pairwise_EMD(torch.from_numpy(smp).cuda(), torch.from_numpy(ref).cuda(), batch_size=3, iters=60).cpu().numpy()
+    want = np.empty((3, 4), np.float32)
+    for i in range(3):
+        d, _ = emd_ref.emd(np.repeat(smp[i:i + 1], 4, 0), ref, 0.005, 60)
+        want[i] = np.sqrt(d).mean(1)
+    assert np.allclose(out, want, rtol=1e-5, atol=1e-7)
