@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="spgan_b200", choices=["spgan_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU port timing (N=1 only runs it)")
-    ap.add_argument("--cpu-batch", type=int, default=16, help="clouds in the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="clouds per step of the CPU sample (0 = the full batch)")
+    ap.add_argument("--cpu-steps", type=int, default=2, help="timed steps of the CPU sample (after one warm-up)")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--engine", type=int, default=None, help="spgan_gemm engine (0 fp32 CUDA cores, 1 tcgen05)")
@@ -110,22 +111,29 @@ def cpu_step_time(batch, points, steps, warmup, seed=123):
 
 
 def run_reference(args, real_stdout):
+    """The reference arm: the full configs[2] batch (B clouds) every step, for the step count asked for
+    (about 13 s per step on 16 host cores: 25 steps fit the driver's window).  Only if the projected run
+    would pass SPGAN_REF_BUDGET_S (default 1500 s) is the per-step batch cut, and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: pick the per-step batch so that the whole run stays within a few minutes
-    t_probe, cores = cpu_step_time(2, args.points, 1, 0)
-    budget = 150.0
-    b = int(budget / max(1e-3, (args.steps + args.warmup) * t_probe / 2.0))
-    b = max(2, min(args.batch, b))
-    t, cores = cpu_step_time(b, args.points, args.steps, args.warmup)
+    budget = float(os.environ.get("SPGAN_REF_BUDGET_S", "1500"))
+    b = args.batch
+    t_probe, cores = cpu_step_time(b, args.points, 1, 0)          # also serves as a first warm-up of the host
+    n_more = args.steps + max(0, args.warmup - 1)
+    if n_more * t_probe > budget:
+        b = max(2, int(b * budget / (n_more * t_probe)))
+    if b == args.batch:
+        t, cores = cpu_step_time(b, args.points, args.steps, max(0, args.warmup - 1))
+    else:
+        t, cores = cpu_step_time(b, args.points, args.steps, args.warmup)
     value = b / t
     sample = "each step = one full WGAN-GP step on %d of the %d clouds (N=%d)" % (b, args.batch, args.points)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[2]: full G+D WGAN-GP step, Chair synthetic, N=%d B=%d" % (args.points, args.batch),
-                       "parallelism": "cpu", "l2": "n/a (CPU)"},
+                       "parallelism": "cpu", "l2": "n/a (CPU)", "batch_per_step": b, "same_config": b == args.batch},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -160,9 +168,14 @@ def main():
         real_stdout.flush()
         sys.stdout.flush()
         sys.stderr.flush()
-    # leave without interpreter / NCCL teardown: destroying a process group whose collectives live inside a
-    # captured CUDA graph can block; every rank has passed the final barrier by now
-    os._exit(0)
+    # Normal interpreter exit (the process group was destroyed inside run_gpu after the captured graph was dropped).
+    # A watchdog covers the one thing that cannot be allowed: a teardown that blocks after the JSON line is out.
+    def _watchdog():
+        time.sleep(60.0)
+        sys.stderr.write("bench.py: teardown still running after 60 s, leaving\n")
+        sys.stderr.flush()
+        os._exit(0)
+    threading.Thread(target=_watchdog, daemon=True).start()
 
 
 def run_gpu(args, real_stdout):
@@ -282,6 +295,36 @@ def run_gpu(args, real_stdout):
     ms_e2e = timed(e2e_step, args.steps) if not minimal else float("nan")
     e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps}
+
+    # ---- secondary end-to-end figure, the way the reference's train.py feeds the step: the latent is
+    # generated on the host as one vector per cloud and TILED over the N points (model.py:122-131: 67 MB per
+    # generator forward, pageable memory), shipped with .cuda() twice per step (model.py:246,270), and the three
+    # losses are read with .item() (model.py:282-286).  The compute is the same graph replay.
+    e2e_train_py = None
+    if not minimal:
+        rng_t = np.random.default_rng(7 + rank)
+
+        def noise_generator():                                            # model.py:122-131
+            nz_ = rng_t.normal(0, 0.2, (B, 1, NZ)).astype(np.float32)
+            return torch.from_numpy(np.tile(nz_, (1, N, 1)))
+
+        def train_py_step(i):
+            zd = noise_generator().to(dev)                                # pageable -> device, synchronous
+            zg = noise_generator().to(dev)
+            d = host[i % n_pool]
+            if use_graph:
+                out = trainer.replay(z_d=zd, z_g=zg, real=d["real"].transpose(2, 1), alpha=d["alpha"])
+            else:
+                out = trainer.step(x, zd, zg, d["real"].to(dev).transpose(2, 1), alpha=d["alpha"].to(dev))
+            losses.append([t.item() for t in out])
+
+        n_tp = max(3, min(args.steps, 10))
+        ms_tp = timed(train_py_step, n_tp)
+        e2e_train_py = {"value": world * B * n_tp / (ms_tp / 1e3), "unit": UNIT, "ms_per_step": ms_tp / n_tp,
+                        "steps": n_tp, "h2d_bytes_per_step": 2 * B * N * NZ * 4 + h2d - 2 * B * NZ * 4,
+                        "d2h_bytes_per_step": 12,
+                        "note": "host-side tiled latent (np.tile) + pageable 67 MB H2D twice per step + .item() reads, "
+                                "as Generation/model.py:122-131,246,270,282-286 does"}
 
     # ---- per-kernel device times of one more step (CUDA events around every C-ABI launch)
     roofline, kernel_share, roofline_all, roofline_knn = None, None, None, None
@@ -481,10 +524,12 @@ def run_gpu(args, real_stdout):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_cpu, cores = cpu_step_time(args.cpu_batch, N, 1, 0)
-        cpu_baseline = {"value": args.cpu_batch / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "1 full WGAN-GP step on %d of the %d clouds (N=%d), oracle port of the reference's "
-                                  "torch CPU path" % (args.cpu_batch, B, N), "ms_per_step": 1e3 * t_cpu}
+        cb = args.cpu_batch if args.cpu_batch > 0 else B
+        t_cpu, cores = cpu_step_time(cb, N, args.cpu_steps, 1)
+        cpu_baseline = {"value": cb / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d timed full WGAN-GP steps (after 1 warm-up) on %d of the %d clouds (N=%d), oracle "
+                                  "port of the reference's torch CPU path" % (args.cpu_steps, cb, B, N),
+                        "ms_per_step": 1e3 * t_cpu}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -494,15 +539,20 @@ def run_gpu(args, real_stdout):
                            "global_batch": world * B, "points": N, "k": 10, "parallelism": "dp%d" % world,
                            "sphere": ball_src, "gemm_engine": pkg.ops.GEMM_ENGINE, "cuda_graph": graph_note,
                            "l2": "no flush needed: per-step working set (activations) is several GB >> 126 MB L2"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks, "e2e": e2e, "e2e_train_py": e2e_train_py, "gpu_launches": launches,
                 "host_enqueue_ms_per_step": host_ms[0] if host_ms else None, "roofline": roofline,
                 "roofline_all_gemm": roofline_all, "roofline_knn": roofline_knn, "submetrics": sub,
                 "kernel_share": kernel_share, "cpu_baseline": cpu_baseline,
                 "last_losses": losses[-1] if losses else None}
         print(json.dumps(line), file=real_stdout, flush=True)
+    # ---- orderly teardown: drop the captured graph (it holds the NCCL all-reduces) before the process group
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    trainer.release_graph()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -159,6 +159,26 @@ int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float *A, 
                int64_t ldb, float *C, int64_t ldc, const float *bias, int accumulate, int engine, void *workspace,
                size_t workspace_bytes, spgan_stream_t stream);
 
+/* Fused point-wise product: a conv -> BatchNorm(train) -> LeakyReLU -> conv chain without the normalised tensor or
+ * the statistics pass ever touching HBM (Discriminator.py:55-81 `mlps`/`fc2`, Generator.py:56-62 `conv_w`):
+ *     C[M,N] = pro(A)[M,K] * op(B) (+ bias[N]) (+ C if accumulate)
+ *     pro(a)[r,k] = LeakyReLU_{a_slope}(a[r,k] * a_scale[k] + a_shift[k])      (identity when a_scale == NULL)
+ * and, when col_sum / col_sqsum are given, row-block partial sums of C and C*C per column:
+ *     col_sum[j, n] = sum of C[r, n] over the rows r of block j, j < spgan_gemm_fused_stats_rows(M)
+ * (32-row blocks, a fixed order: the result is deterministic; spgan_bn_finalize turns them into the batch mean /
+ * variance and the next layer's a_scale / a_shift).  A [M,K] row-major with lda % 4 == 0 and 16-byte aligned;
+ * op(B) as in spgan_gemm.  16 <= K <= 256, M >= 128, N >= 16.  sm_100a kernel: TMA-staged fp32 A tiles, operand
+ * split x = hi + 2^-11 lo in fp16 (22 significant bits, 3 tcgen05 MMAs per product), A converted once per
+ * 128-row tile into tensor memory and reused for all N/64 column tiles (csrc/gemm_ts.cu).
+ * spgan_gemm_fused_workspace returns the workspace size in bytes (256-byte aligned buffer), or 0 when the
+ * shape / alignment is not supported (the caller then composes spgan_gemm + spgan_colstats + spgan_norm_apply). */
+size_t spgan_gemm_fused_workspace(int64_t M, int N, int K, const float *A, int64_t lda);
+size_t spgan_gemm_fused_stats_rows(int64_t M);
+int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float *A, int64_t lda, const float *B, int64_t ldb,
+                     float *C, int64_t ldc, const float *bias, int accumulate, const float *a_scale,
+                     const float *a_shift, float a_slope, float *col_sum, float *col_sqsum, void *workspace,
+                     size_t workspace_bytes, spgan_stream_t stream);
+
 /* ------------------------------------------------------------------ elementwise
  * n = element count of flat fp32 tensors unless rows/cols are given. */
 int spgan_fill(float *x, int64_t n, float v, spgan_stream_t stream);

@@ -2,6 +2,7 @@
 // 128 x BN x 16 tiles, 256 threads, 8 x (BN/16) register micro-tiles, register-prefetch double
 // buffering.  transA (wgrad: K = number of points) runs split-K with fp32 atomics.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -285,11 +286,19 @@ int spgan_gemm_simt(int transA, int transB, int64_t M, int N, int K, const float
 
 size_t spgan_gemm_tc_workspace(int N, int K);
 bool spgan_gemm_tc_supported(int transA, int64_t M, int N, int K);
-int spgan_gemm_tc_f16s(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb,
-                       float* C, int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st);
-int spgan_gemm_tc(int mode_bf16, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+int spgan_gemm_tc(int mode, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
                   int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, void* workspace,
                   cudaStream_t st);
+
+size_t spgan_gemm_ts_workspace(int N, int K);
+bool spgan_gemm_ts_supported(int64_t M, int N, int K, const float* A, int64_t lda);
+int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                  int64_t ldc, const float* bias, int accumulate, const float* a_scale, const float* a_shift, float a_slope,
+                  float* col_sum, float* col_sqsum, void* workspace, cudaStream_t st);
+static bool ts_enabled() {
+    static const bool on = [] { const char* e = getenv("SPGAN_TS"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 bool spgan_gemm_tc_tn_supported(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B,
                                 int64_t ldb);
@@ -314,16 +323,17 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
     SPGAN_CHECK_ARG(A && B && C && M >= 0 && N >= 1 && K >= 1);
     SPGAN_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N);
     if (M == 0) return SPGAN_OK;
-    // engine 3 (opt-in): fp16x3 with scaled residuals for the forward / dgrad products (gemm_tc_f16s.cu); weight
-    // gradients and everything the tensor path does not take fall through to engine 1's routes below
-    if (engine == 3 && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
+    // engine 3, K <= 256: the TMEM-resident-A kernel (gemm_ts.cu); SPGAN_TS=0 routes these to gemm_tc.cu instead
+    if (engine == 3 && !transA && workspace != nullptr && ts_enabled() && spgan_gemm_ts_supported(M, N, K, A, lda) &&
+        workspace_bytes >= spgan_gemm_ts_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
+        return spgan_gemm_ts(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, nullptr, 1.f, nullptr,
+                             nullptr, workspace, as_stream(stream));
+    // tcgen05 engines: 1 = TF32x3, 2 = BF16x3, 3 = FP16Sx3 (gemm_tc.cu) for the forward / dgrad products
+    if (engine >= 1 && engine <= 3 && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
         workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
-        return spgan_gemm_tc_f16s(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, as_stream(stream));
-    if (engine == 3) engine = 1;
-    if ((engine == 1 || engine == 2) && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
-        workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
-        return spgan_gemm_tc(engine == 2, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
+        return spgan_gemm_tc(engine - 1, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
                              as_stream(stream));
+    if (engine == 3) engine = 1;          // weight gradients: the TF32x3 transposing kernel for every tensor engine
     // weight gradients: C[M,N] = A^T B with A [K,M], B [K,N], K = #points (TF32x3 for both tensor engines)
     if ((engine == 1 || engine == 2) && workspace != nullptr && workspace_bytes >= 256 && transA && !transB &&
         bias == nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
@@ -334,4 +344,25 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
         return spgan_gemm_tn_skinny(M, N, K, A, lda, B, ldb, C, ldc, accumulate, as_stream(stream));
     return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream),
                            workspace, workspace_bytes);
+}
+
+extern "C" size_t spgan_gemm_fused_workspace(int64_t M, int N, int K, const float* A, int64_t lda) {
+    if (N < 1 || K < 1 || !spgan_gemm_ts_supported(M, N, K, A, lda)) return 0;
+    return spgan_gemm_ts_workspace(N, K);
+}
+
+extern "C" size_t spgan_gemm_fused_stats_rows(int64_t M) { return M <= 0 ? 0 : (size_t)(4 * ((M + 127) / 128)); }
+
+extern "C" int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                                int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate,
+                                const float* a_scale, const float* a_shift, float a_slope, float* col_sum,
+                                float* col_sqsum, void* workspace, size_t workspace_bytes, spgan_stream_t stream) {
+    SPGAN_CHECK_ARG(A && B && C && workspace && M >= 1 && N >= 1 && K >= 1);
+    SPGAN_CHECK_ARG(lda >= K && ldb >= (transB ? K : N) && ldc >= N);
+    SPGAN_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr) && (col_sum == nullptr) == (col_sqsum == nullptr));
+    if (!spgan_gemm_ts_supported(M, N, K, A, lda) || workspace_bytes < spgan_gemm_ts_workspace(N, K) ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+        return SPGAN_E_UNSUPPORTED;
+    return spgan_gemm_ts(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, a_scale, a_shift, a_slope, col_sum,
+                         col_sqsum, workspace, as_stream(stream));
 }

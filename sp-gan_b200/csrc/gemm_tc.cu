@@ -8,6 +8,12 @@
 //   BF16 mode (engine 2, "fast"): hi = trunc_bf16(x), lo = rn_bf16(x - hi): ~2^-16 per product,
 //       twice the MMA rate; NOT used by default because train-mode BatchNorm and the gradient
 //       penalty amplify it to the 1e-3 parity bar (DESIGN.md "GEMM precision").
+//   FP16S mode (engine 3): hi = rn_f16(x), lo = rn_f16((x - hi) * 2^11): fp16 carries the same 11 significant
+//       bits as tf32, so the split is as fine as TF32 mode (22 bits) at the kind::f16 MMA rate (2x tf32).  The
+//       residual is scaled by 2^11 so that it stays a NORMAL fp16 number whatever |x| is; the cross terms
+//       therefore accumulate 2^11 too large in their own TMEM accumulator and the epilogue forms
+//       main + 2^-11 * cross.  Needs |x| < 65504 (fp16 range).  Validated on B200 in round 2
+//       (tests/test_gpu_gemm_tc.py: same error class as TF32x3 against fp64).
 //
 // Structure (one persistent CTA per SM, 20 warps):
 //   warps 0-7   epilogue : tcgen05.ld accumulator rows from TMEM -> shared transpose -> (+bias, +C)
@@ -22,6 +28,7 @@
 // Every mbarrier wait is bounded; on timeout the kernel raises a status word instead of hanging.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -43,8 +50,12 @@ constexpr int EPI_LD = 32;                  // epilogue staging tile: 32 x 32 fl
 #define SPGAN_TC_CONSUMER_FENCE_DEFAULT 0
 #endif
 
-template <int BN, bool TF32>
+enum : int { MODE_TF32 = 0, MODE_BF16 = 1, MODE_F16S = 2 };
+
+template <int BN, int MODE>
 struct Cfg {
+    static constexpr bool TF32 = MODE == MODE_TF32;
+    static constexpr bool TWOACC = MODE != MODE_BF16;    // separate accumulator for the cross terms
     static constexpr int BK = TF32 ? 32 : 64;            // elements per k-block
     static constexpr int CHUNK = TF32 ? 4 : 8;           // elements per 16-byte chunk
     static constexpr int A_BYTES = BM * 128;             // one half (hi or lo)
@@ -54,7 +65,7 @@ struct Cfg {
     // TF32 mode keeps the small cross terms (hi*lo + lo*hi) in a second accumulator: the tensor core adds
     // into TMEM with truncation, so the error grows with the number of accumulations into the LARGE sum;
     // this cuts that count by 3 (measured: rms error ~7e-9*K -> ~2.4e-9*K).
-    static constexpr int NACC = TF32 ? 2 : 1;
+    static constexpr int NACC = TWOACC ? 2 : 1;
     static constexpr int TMEM_COLS = 2 * NACC * BN;      // two tile buffers; power of two <= 512
     static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
@@ -76,8 +87,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // instruction descriptor: D=f32 [4,6), A format [7,10), B format [10,13) (1 = bf16, 2 = tf32), both K-major,
 // N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool tf32) {
-    const uint32_t fmt = tf32 ? 2u : 1u;
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int mode) {
+    const uint32_t fmt = mode == MODE_TF32 ? 2u : (mode == MODE_F16S ? 0u : 1u);    // kind::f16 formats: 0 = f16, 1 = bf16
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -100,18 +111,35 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// 8 fp32 -> 8 fp16 "hi" (round to nearest) + 8 fp16 "lo" = rn((x - hi) * 2^11), element 0 in the low half
+__device__ __forceinline__ void split8_f16s(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        float h0, h1;
+        asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+            : "=f"(h0), "=f"(h1) : "r"(h[i]));
+        const float r0 = (v[2 * i] - h0) * 2048.f, r1 = (v[2 * i + 1] - h1) * 2048.f;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(r1), "f"(r0));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // CF ("consumer fence"): where the generic->async proxy fence for the operand tiles is executed.  false: by every
 // producer thread before its mbarrier arrive (the textbook placement).  true: once per k-block by the MMA-issuing
 // thread after its acquire of the full barrier.  fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and
 // the MEMBAR makes a producer wait for ITS OWN outstanding global prefetch loads: with the fence on the producer
 // side every k-block costs a full memory latency no matter how deep the prefetch ring is.
-template <int BN, bool TF32, int PF, bool CF>
+template <int BN, int MODE, int PF, bool CF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda,
                const unsigned char* __restrict__ Bhi, const unsigned char* __restrict__ Blo, int Kp, int n_tiles,
                float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int accumulate, int* status,
                bool vecA, bool vecC) {
-    using cfg = Cfg<BN, TF32>;
+    using cfg = Cfg<BN, MODE>;
+    constexpr bool TF32 = cfg::TF32, TWOACC = cfg::TWOACC;
     constexpr int BK = cfg::BK, CHUNK = cfg::CHUNK, ESZ = TF32 ? 4 : 2;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -120,7 +148,8 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * cfg::STAGES + 4);
     float* epi_smem = reinterpret_cast<float*>(smem + cfg::STAGES * cfg::STAGE_BYTES + 256);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (see tc::elect_one)
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (cfg::STAGES + s); };
@@ -139,7 +168,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int m_tiles = (int)((M + BM - 1) / BM);
     const int KB = Kp / BK;
@@ -230,7 +259,8 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                     } else {
                         const float v[8] = {buf[s][2 * j].x, buf[s][2 * j].y, buf[s][2 * j].z, buf[s][2 * j].w,
                                             buf[s][2 * j + 1].x, buf[s][2 * j + 1].y, buf[s][2 * j + 1].z, buf[s][2 * j + 1].w};
-                        split8(v, hi, lo);
+                        if constexpr (MODE == MODE_F16S) split8_f16s(v, hi, lo);
+                        else split8(v, hi, lo);
                     }
                     *reinterpret_cast<uint4*>(sa_hi + soff[j]) = hi;
                     *reinterpret_cast<uint4*>(sa_lo + soff[j]) = lo;
@@ -285,8 +315,8 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
         }
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer
-        constexpr uint32_t idesc = make_idesc(BM, BN, TF32);
-        constexpr uint32_t idesc2 = make_idesc(BM, (TF32 && BN <= 128) ? 2 * BN : BN, TF32);
+        constexpr uint32_t idesc = make_idesc(BM, BN, MODE);
+        constexpr uint32_t idesc2 = make_idesc(BM, (TWOACC && BN <= 128) ? 2 * BN : BN, MODE);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         bool ok = true;
@@ -294,11 +324,11 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
             if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1, vstatus)) { ok = false; break; }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(acc * cfg::NACC * BN);
-            const uint32_t tmem_x = TF32 ? tmem_d + BN : tmem_d;          // cross-term accumulator
+            const uint32_t tmem_x = TWOACC ? tmem_d + BN : tmem_d;        // cross-term accumulator
             for (int kb = 0; kb < KB; ++kb) {
                 if (!mbar_wait(full_bar(stage), phase, vstatus)) { ok = false; break; }
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     if constexpr (CF) fence_proxy_async();        // acquired the producers' writes: hand them to the async proxy
                     const uint32_t sa_hi = smem_u32(smem + stage * cfg::STAGE_BYTES);
                     const uint32_t sa_lo = sa_hi + cfg::A_BYTES;
@@ -316,6 +346,11 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                             // shared memory twice instead of three times
                             umma<true>(tmem_d, dah + adv, dbh + adv, idesc2, first);
                             umma<true>(tmem_x, dal + adv, dbh + adv, idesc, 1u);
+                        } else if constexpr (MODE == MODE_F16S) {
+                            // same two-instruction scheme at the kind::f16 rate; both cross terms carry the 2^11
+                            // scale of the residuals
+                            umma<false>(tmem_d, dah + adv, dbh + adv, idesc2, first);
+                            umma<false>(tmem_x, dal + adv, dbh + adv, idesc, 1u);
                         } else {
                             umma<false>(tmem_d, dah + adv, dbh + adv, idesc, first);
                             umma<false>(tmem_d, dah + adv, dbl + adv, idesc, 1u);
@@ -328,7 +363,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                 if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
             }
             if (!ok) break;
-            if (lane == 0) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            if (elect_one()) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
             __syncwarp();
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -364,13 +399,18 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
                 {
                     uint32_t rv[32], rw[32];
                     tmem_ld32_issue(taddr + c0, rv);    // all lanes participate (sync.aligned); one wait for both
-                    if constexpr (TF32) tmem_ld32_issue(taddr + BN + c0, rw);     // cross-term accumulator
+                    if constexpr (TWOACC) tmem_ld32_issue(taddr + BN + c0, rw);   // cross-term accumulator
                     tmem_ld_wait();
                     tmem_pin32(rv);
                     if constexpr (TF32) {
                         tmem_pin32(rw);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]) + __uint_as_float(rw[j]);
+                    } else if constexpr (MODE == MODE_F16S) {
+                        tmem_pin32(rw);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = fmaf(__uint_as_float(rw[j]), 1.f / 2048.f, __uint_as_float(rv[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]);
@@ -448,7 +488,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
 }
 
 // B (weights) -> zero-padded hi / lo terms, K-major [Npad, Kp] (bf16 or tf32-in-fp32); clears the status word
-template <bool TF32>
+template <int MODE>
 __global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int transB, int N, int K, int Npad, int Kp,
                                   void* __restrict__ hi_, void* __restrict__ lo_, int* status) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
@@ -457,11 +497,16 @@ __global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int 
         const int n = (int)(i / Kp), k = (int)(i % Kp);
         float v = 0.f;
         if (n < N && k < K) v = transB ? __ldg(B + (int64_t)n * ldb + k) : __ldg(B + (int64_t)k * ldb + n);
-        if constexpr (TF32) {
+        if constexpr (MODE == MODE_TF32) {
             const uint32_t h = tf32_rna_bits(v);
             const uint32_t l = tf32_rna_bits(v - __uint_as_float(h));
             reinterpret_cast<uint32_t*>(hi_)[i] = h;
             reinterpret_cast<uint32_t*>(lo_)[i] = l;
+        } else if constexpr (MODE == MODE_F16S) {
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn((v - __half2float(h)) * 2048.f);
+            reinterpret_cast<uint16_t*>(hi_)[i] = __half_as_ushort(h);
+            reinterpret_cast<uint16_t*>(lo_)[i] = __half_as_ushort(l);
         } else {
             const uint32_t u = __float_as_uint(v);
             const float r = v - __uint_as_float(u & 0xffff0000u);
@@ -476,11 +521,11 @@ __global__ void presplit_b_kernel(const float* __restrict__ B, int64_t ldb, int 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-template <int BN, bool TF32, int PF, bool CF>
+template <int BN, int MODE, int PF, bool CF>
 int launch_tc_pf(int64_t M, int N, int K, const float* A, int64_t lda, const unsigned char* hi, const unsigned char* lo,
                  int Kp, int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
-    using cfg = Cfg<BN, TF32>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, TF32, PF, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    using cfg = Cfg<BN, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, PF, CF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int n_tiles = Npad / BN;
@@ -488,7 +533,7 @@ int launch_tc_pf(int64_t M, int N, int K, const float* A, int64_t lda, const uns
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
     const bool vecA = (lda % 4 == 0) && aligned16(A);
     const bool vecC = (ldc % 4 == 0) && aligned16(C) && (bias == nullptr || aligned16(bias));
-    gemm_tc_kernel<BN, TF32, PF, CF><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc,
+    gemm_tc_kernel<BN, MODE, PF, CF><<<grid, TC_THREADS, cfg::SMEM_BYTES, st>>>(M, N, K, A, lda, hi, lo, Kp, n_tiles, C, ldc,
                                                                              bias, accumulate, status, vecA, vecC);
     return spgan_launch_status();
 }
@@ -515,37 +560,39 @@ inline bool tc_consumer_fence() {
 }
 
 #define SPGAN_TC_ARGS M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st
-template <int BN, bool TF32>
+template <int BN, int MODE>
 int launch_tc(int64_t M, int N, int K, const float* A, int64_t lda, const unsigned char* hi, const unsigned char* lo,
               int Kp, int Npad, float* C, int64_t ldc, const float* bias, int accumulate, int* status, cudaStream_t st) {
     const bool cf = tc_consumer_fence();
-    if constexpr (TF32) {
+    if constexpr (MODE == MODE_TF32) {
         const int pf = tc_prefetch_sets();
-        if (pf == 3) return cf ? launch_tc_pf<BN, TF32, 3, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, TF32, 3, false>(SPGAN_TC_ARGS);
-        if (pf == 4) return cf ? launch_tc_pf<BN, TF32, 4, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, TF32, 4, false>(SPGAN_TC_ARGS);
+        if (pf == 3) return cf ? launch_tc_pf<BN, MODE, 3, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, MODE, 3, false>(SPGAN_TC_ARGS);
+        if (pf == 4) return cf ? launch_tc_pf<BN, MODE, 4, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, MODE, 4, false>(SPGAN_TC_ARGS);
     }
-    return cf ? launch_tc_pf<BN, TF32, 2, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, TF32, 2, false>(SPGAN_TC_ARGS);
+    // 2-byte modes: 8 floats per task, two register sets
+    return cf ? launch_tc_pf<BN, MODE, 2, true>(SPGAN_TC_ARGS) : launch_tc_pf<BN, MODE, 2, false>(SPGAN_TC_ARGS);
 }
 #undef SPGAN_TC_ARGS
 
-template <bool TF32>
+template <int MODE>
 int run_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
            int64_t ldc, const float* bias, int accumulate, void* workspace, cudaStream_t st) {
+    constexpr bool TF32 = MODE == MODE_TF32;
     constexpr int BK = TF32 ? 32 : 64;
     constexpr size_t ESZ = TF32 ? 4 : 2;
-    const int BN = N <= 64 ? 64 : ((N <= 128 || TF32) ? 128 : 256);     // TF32: two accumulators per tile
+    const int BN = N <= 64 ? 64 : ((N <= 128 || MODE != MODE_BF16) ? 128 : 256);     // two accumulators per tile: BN <= 128
     const int Npad = (int)align_up((size_t)N, BN), Kp = (int)align_up((size_t)K, BK);
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
     unsigned char* hi = ws + 256;
     unsigned char* lo = hi + align_up(align_up((size_t)N, 256) * Kp * ESZ, 256);
-    presplit_b_kernel<TF32><<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, Npad, Kp, hi, lo, status);
+    presplit_b_kernel<MODE><<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, Npad, Kp, hi, lo, status);
     int rc = spgan_launch_status();
     if (rc != SPGAN_OK) return rc;
-    if (BN == 64) return launch_tc<64, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
-    if (BN == 128) return launch_tc<128, TF32>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
-    if constexpr (!TF32)
-        return launch_tc<256, false>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    if (BN == 64) return launch_tc<64, MODE>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    if (BN == 128) return launch_tc<128, MODE>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
+    if constexpr (MODE == MODE_BF16)
+        return launch_tc<256, MODE_BF16>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
     return SPGAN_E_UNSUPPORTED;
 }
 
@@ -561,9 +608,11 @@ bool spgan_gemm_tc_supported(int transA, int64_t M, int N, int K) {
     return !transA && M >= 128 && N >= 16 && K >= 16;
 }
 
-int spgan_gemm_tc(int mode_bf16, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+// mode: 0 = TF32x3 (engine 1), 1 = BF16x3 (engine 2), 2 = FP16Sx3 (engine 3)
+int spgan_gemm_tc(int mode, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
                   int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, void* workspace,
                   cudaStream_t st) {
-    if (mode_bf16) return run_tc<false>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
-    return run_tc<true>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
+    if (mode == MODE_BF16) return run_tc<MODE_BF16>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
+    if (mode == MODE_F16S) return run_tc<MODE_F16S>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
+    return run_tc<MODE_TF32>(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace, st);
 }

@@ -67,7 +67,8 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * cfg::STAGES + 2);
     float* epi_smem = reinterpret_cast<float*>(smem + cfg::STAGES * cfg::STAGE_BYTES + 256);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler (see tc::elect_one)
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (cfg::STAGES + s); };
@@ -84,7 +85,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int64_t tiles = (int64_t)m_tiles * n_tiles;
     const int64_t units = tiles * k_chunks;
@@ -202,7 +203,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
             for (int kb = 0; kb < kblocks; ++kb) {
                 if (!mbar_wait(full_bar(stage), phase, vstatus)) { ok = false; break; }
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sa_hi = smem_u32(smem + stage * cfg::STAGE_BYTES);
                     const uint32_t sa_lo = sa_hi + cfg::A_BYTES;
                     const uint32_t sb_hi = sa_lo + cfg::A_BYTES;
@@ -229,7 +230,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
                 if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
             }
             if (!ok) break;
-            if (lane == 0) umma_commit(tfull_bar);
+            if (elect_one()) umma_commit(tfull_bar);
             __syncwarp();
             tphase ^= 1;
         }

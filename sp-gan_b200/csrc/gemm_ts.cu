@@ -1,0 +1,541 @@
+// Fused point-wise GEMM for the activation x small-weight products of the step (every Conv1d(k=1) / Conv2d(1x1) /
+// Linear with K <= 256, Generator.py:56-71,107-135, Discriminator.py:55-94):
+//
+//     C[M,N] = pro(A)[M,K] * W^T (+ bias) (+ C),     pro(a)[r,k] = LeakyReLU_slope(a[r,k] * scale[k] + shift[k])
+//     (+ per-column partial sums of C and C^2 for the train-mode BatchNorm that follows)
+//
+// fp32 in / fp32 out, FP16S operand split (gemm_tc.cu): x = hi + 2^-11 lo with hi, lo in fp16, three kind::f16 MMAs
+// per product (hi*hi | hi*lo in one N = 2*BN instruction, lo*hi in a second), main and cross terms in separate fp32
+// TMEM accumulators, 22 significant bits per operand.
+//
+// What differs from gemm_tc.cu (the streaming SS kernel, still used for K > 256):
+//   * The fp32 A tile reaches shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle, out-of-bounds rows and
+//     columns zero-filled by the hardware) -- no register prefetch ring, no generic-proxy stores to operand tiles,
+//     no proxy fences on the load path.
+//   * Converter warps read the staged tile ROW PER THREAD (TMEM lane = matrix row), apply the prologue in registers
+//     (the BatchNorm + LeakyReLU of the producing layer: Generator.py:58-62, Discriminator.py:57-64 -- the
+//     normalised tensor is never written to HBM), split, and write hi / lo straight into TENSOR MEMORY with
+//     tcgen05.st.  The MMAs take A from TMEM (tcgen05.mma "TS" form): the A operand costs no shared-memory
+//     bandwidth, which a 128 x 128 SS tile saturates (8 KB per 64-cycle instruction = 128 B/clk).
+//   * A is converted ONCE per 128-row tile and stays resident in TMEM while the CTA walks all N / 64 column tiles
+//     (the SS kernel re-reads and re-converts A for every column tile: 8 times for the critic's 256 -> 1024 layer).
+//   * The weight tiles [W_hi ; W_lo] (pre-split, 64 + 64 rows x 64 k) arrive by TMA, one instruction per tile.
+//   * All mbarrier arrivals are one elected lane per warp (the SS kernel's 352 per-thread arrivals per k-block
+//     serialise on one shared-memory word).
+//   * Epilogue: bias, optional C +=, optional per-(tile, lane-quarter) column sums / sums of squares written as
+//     deterministic partial rows (finalised in fp64 by spgan_bn_finalize) -- the BatchNorm statistics pass over
+//     the output disappears.
+//
+// TMEM map (512 columns): [0,256) two accumulator buffers x (main 64 | cross 64); [256,512) A operand: one region
+// of up to 4 k-blocks (K <= 256) or two regions of 2 k-blocks (K <= 128, so that the conversion of the next row
+// tile overlaps the MMAs of the current one).  A k-block = 64 k = 32 columns of packed hi pairs + 32 of lo pairs.
+//
+// Warp roles (19 warps): 0-7 converters (lane quarter = warp % 4, k-half = warp / 4), 8-15 epilogue (same split over
+// the 64 output columns), 16 MMA issuer, 17 TMA producer for A, 18 TMA producer for W.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 64, BK = 64;
+constexpr int CVT_WARP0 = 0, EPI_WARP0 = 8, MMA_WARP = 16, TMA_A_WARP = 17, TMA_B_WARP = 18;
+constexpr int TS_THREADS = 19 * 32;
+constexpr int A_STAGES = 3;                       // staged fp32 k-blocks: two 128-row x 32-float boxes each
+constexpr int A_STAGE_BYTES = 2 * BM * 128;       // 32 KB
+constexpr int B_STAGES = 5;                       // [W_hi ; W_lo] tiles: 128 rows x 128 bytes
+constexpr int B_STAGE_BYTES = 2 * BN * 128;       // 16 KB
+constexpr int EPI_BYTES = 8 * 32 * 32 * 4;        // one 32 x 32 fp32 transpose tile per epilogue warp
+constexpr int MAX_KB = 4;                         // K <= 256
+constexpr int TAB_BYTES = 2 * MAX_KB * BK * 4;    // prologue scale / shift tables
+constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + EPI_BYTES + TAB_BYTES + 512 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_A0 = 256;
+
+// barrier slots
+constexpr int BAR_SA_FULL = 0;                        // [A_STAGES] TMA landed (tx)
+constexpr int BAR_SA_EMPTY = BAR_SA_FULL + A_STAGES;  // [A_STAGES] 8 converter warps done reading
+constexpr int BAR_TA_FULL = BAR_SA_EMPTY + A_STAGES;  // [4]        A k-block in TMEM (8 converter warps)
+constexpr int BAR_TA_EMPTY = BAR_TA_FULL + 4;         // [2]        A region free (tcgen05.commit)
+constexpr int BAR_SB_FULL = BAR_TA_EMPTY + 2;         // [B_STAGES] TMA landed (tx)
+constexpr int BAR_SB_EMPTY = BAR_SB_FULL + B_STAGES;  // [B_STAGES] tcgen05.commit
+constexpr int BAR_D_FULL = BAR_SB_EMPTY + B_STAGES;   // [2]        accumulator complete (commit)
+constexpr int BAR_D_EMPTY = BAR_D_FULL + 2;           // [2]        8 epilogue warps have read it
+constexpr int NUM_BARS = BAR_D_EMPTY + 2;
+static_assert(NUM_BARS * 8 + 16 <= 512, "barrier block");
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::f16
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (the layout TMA writes with SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// one elected lane per warp arrives, after the whole warp has reached this point
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+struct TsParams {
+    int64_t M;
+    int N, K;
+    float* C;
+    int64_t ldc;
+    const float* bias;
+    int accumulate;
+    const float* a_scale;      // prologue tables [K] (both NULL: identity)
+    const float* a_shift;
+    float a_slope;             // LeakyReLU slope of the prologue (1 = none)
+    float* col_sum;            // epilogue partials [4 * m_tiles, N] (both NULL: none)
+    float* col_sqsum;
+    int* status;
+    int vecC;
+};
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TsParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smA = smem;
+    unsigned char* smB = smA + A_STAGES * A_STAGE_BYTES;
+    float* epi_smem = reinterpret_cast<float*>(smB + B_STAGES * B_STAGE_BYTES);
+    float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(epi_smem) + EPI_BYTES);      // scale[256], shift[256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tab) + TAB_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: role branches are uniform
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int slot) { return bar0 + 8u * slot; };
+    volatile int* vstatus = p.status;
+
+    const int KB = (p.K + BK - 1) / BK;                   // 1..4
+    const int NREG = KB <= 2 ? 2 : 1;                      // A regions in TMEM
+    const int m_tiles = (int)((p.M + BM - 1) / BM);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const bool has_pro = p.a_scale != nullptr;
+
+    if (tid == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(BAR_SA_FULL + s), 1); mbar_init(bar(BAR_SA_EMPTY + s), 8); }
+        for (int s = 0; s < 4; ++s) mbar_init(bar(BAR_TA_FULL + s), 8);
+        for (int s = 0; s < 2; ++s) mbar_init(bar(BAR_TA_EMPTY + s), 1);
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bar(BAR_SB_FULL + s), 1); mbar_init(bar(BAR_SB_EMPTY + s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_D_FULL + s), 1); mbar_init(bar(BAR_D_EMPTY + s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // prologue tables, zero beyond K: a zero-filled (out-of-bounds) column must stay zero after the prologue
+    if (has_pro) {
+        for (int k = tid; k < MAX_KB * BK; k += TS_THREADS) {
+            tab[k] = k < p.K ? __ldg(p.a_scale + k) : 0.f;
+            tab[MAX_KB * BK + k] = k < p.K ? __ldg(p.a_shift + k) : 0.f;
+        }
+    }
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == TMA_A_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    if (warp == TMA_B_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // The CTA owns the SM (launch bounds, ~210 KB of shared memory) and asks for all 512 columns, so the allocation
+    // starts at lane 0 / column 0: the MMA issuer relies on it to keep its operand addresses warp-uniform constants.
+    if (tmem_base != 0) __trap();
+
+    if (warp == TMA_A_WARP) {
+        // ================================================================ TMA producer: fp32 A k-blocks
+        // (whole warp walks the loop, one elected lane issues: see elect_one)
+        const uint32_t sA0 = smem_u32(smA);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bar(BAR_SA_EMPTY + stage), phase ^ 1, vstatus);
+                if (elect_one()) {
+                    const uint32_t dst = sA0 + (uint32_t)(stage * A_STAGE_BYTES);
+                    mbar_expect_tx(bar(BAR_SA_FULL + stage), A_STAGE_BYTES);
+                    tma_load_2d(dst, &tmA, kb * BK, mt * BM, bar(BAR_SA_FULL + stage));
+                    tma_load_2d(dst + BM * 128, &tmA, kb * BK + 32, mt * BM, bar(BAR_SA_FULL + stage));
+                }
+                __syncwarp();
+                if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == TMA_B_WARP) {
+        // ================================================================ TMA producer: [W_hi ; W_lo] tiles
+        const uint32_t sB0 = smem_u32(smB);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar(BAR_SB_EMPTY + stage), phase ^ 1, vstatus);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar(BAR_SB_FULL + stage), B_STAGE_BYTES);
+                        tma_load_2d(sB0 + (uint32_t)(stage * B_STAGE_BYTES), &tmB, kb * BK, nt * 2 * BN, bar(BAR_SB_FULL + stage));
+                    }
+                    __syncwarp();
+                    if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ================================================================ MMA issuer
+        constexpr uint32_t idesc_main = make_idesc_f16(BM, 2 * BN);     // [main | cross] += A_hi x [W_hi ; W_lo]
+        constexpr uint32_t idesc_x = make_idesc_f16(BM, BN);            // cross += A_lo x W_hi
+        // everything below is warp-uniform: the whole warp walks the loops, one elected lane issues (see elect_one)
+        const uint32_t sB0 = smem_u32(smB);
+        int sb = 0, buf = 0;
+        uint32_t sb_phase = 0, d_phase = 0;
+        uint32_t ta_phase[2] = {0, 0};
+        int it = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+            const int g = NREG == 2 ? (it & 1) : 0;
+            const uint32_t a_base = TMEM_A0 + (uint32_t)(g * 128);         // tmem_base == 0 (checked at start-up)
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                mbar_wait(bar(BAR_D_EMPTY + buf), d_phase ^ 1, vstatus);
+                tc_fence_after();
+                const uint32_t d_main = (uint32_t)(buf * 2 * BN);
+                const uint32_t d_x = d_main + BN;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (nt == 0) mbar_wait(bar(BAR_TA_FULL + g * 2 * (NREG - 1) + kb), ta_phase[g], vstatus);
+                    mbar_wait(bar(BAR_SB_FULL + sb), sb_phase, vstatus);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t bd = make_desc_sw128(sB0 + (uint32_t)(sb * B_STAGE_BYTES));
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {                    // 4 k-steps of 16
+                            const uint32_t a_hi = a_base + (uint32_t)(kb * 64 + s * 8);
+                            umma_ts(d_main, a_hi, bd + (uint64_t)(s * 2), idesc_main, (kb > 0 || s > 0) ? 1u : 0u);
+                            umma_ts(d_x, a_hi + 32, bd + (uint64_t)(s * 2), idesc_x, 1u);
+                        }
+                        umma_commit(bar(BAR_SB_EMPTY + sb));
+                    }
+                    __syncwarp();
+                    if (++sb == B_STAGES) { sb = 0; sb_phase ^= 1; }
+                }
+                if (elect_one()) {
+                    umma_commit(bar(BAR_D_FULL + buf));
+                    if (nt == n_tiles - 1) umma_commit(bar(BAR_TA_EMPTY + g));      // A region may be overwritten
+                }
+                __syncwarp();
+                buf ^= 1;
+                if (buf == 0) d_phase ^= 1;
+            }
+            ta_phase[g] ^= 1;
+        }
+    } else if (warp < EPI_WARP0) {
+        // ================================================================ converters: staged fp32 -> prologue -> hi/lo -> TMEM
+        const int q = warp & 3, h = warp >> 2;             // lane quarter (rows 32q..32q+31), k-half of the k-block
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const float slope = p.a_slope;
+        int stage = 0;
+        uint32_t sa_phase = 0;
+        uint32_t te_phase[2] = {0, 0};
+        int it = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+            const int g = NREG == 2 ? (it & 1) : 0;
+            // the region's previous occupant (NREG tiles ago) must have been consumed by its last MMA
+            if (it >= NREG) {
+                mbar_wait(bar(BAR_TA_EMPTY + g), te_phase[g], vstatus);
+                te_phase[g] ^= 1;
+                tc_fence_after();
+            }
+            const uint32_t a_base = tmem_base + TMEM_A0 + (uint32_t)(g * 128) + lane_addr;
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(bar(BAR_SA_FULL + stage), sa_phase, vstatus);
+                const unsigned char* box = smA + stage * A_STAGE_BYTES + h * (BM * 128) + row * 128;
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 t = *reinterpret_cast<const float4*>(box + ((c ^ (row & 7)) << 4));
+                    v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+                }
+                if (has_pro) {
+                    const float4* sc = reinterpret_cast<const float4*>(tab + kb * BK + h * 32);
+                    const float4* sh = reinterpret_cast<const float4*>(tab + MAX_KB * BK + kb * BK + h * 32);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 a = sc[c], b = sh[c];
+                        float y;
+                        y = fmaf(v[4 * c], a.x, b.x);     v[4 * c] = fmaxf(y, y * slope);
+                        y = fmaf(v[4 * c + 1], a.y, b.y); v[4 * c + 1] = fmaxf(y, y * slope);
+                        y = fmaf(v[4 * c + 2], a.z, b.z); v[4 * c + 2] = fmaxf(y, y * slope);
+                        y = fmaf(v[4 * c + 3], a.w, b.w); v[4 * c + 3] = fmaxf(y, y * slope);
+                    }
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+                    float h0, h1;
+                    asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+                        : "=f"(h0), "=f"(h1) : "r"(hi[i]));
+                    const float r0 = (v[2 * i] - h0) * 2048.f, r1 = (v[2 * i + 1] - h1) * 2048.f;
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(r1), "f"(r0));
+                }
+                // every value of the staged box is in registers (the conversions above consumed the loads):
+                // hand the stage back to the TMA producer
+                warp_arrive(bar(BAR_SA_EMPTY + stage), lane);
+                tmem_st16(a_base + (uint32_t)(kb * 64 + h * 16), hi);
+                tmem_st16(a_base + (uint32_t)(kb * 64 + 32 + h * 16), lo);
+                tmem_st_wait();
+                tc_fence_before();
+                warp_arrive(bar(BAR_TA_FULL + g * 2 * (NREG - 1) + kb), lane);
+                if (++stage == A_STAGES) { stage = 0; sa_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================================================ epilogue (warps 8..15)
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, h = ew >> 2;                 // lane quarter, 32-column half of the 64-column tile
+        float* T = epi_smem + ew * (32 * 32);
+        const bool want_stats = p.col_sum != nullptr;
+        int buf = 0;
+        uint32_t d_phase = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+            const int64_t m0 = (int64_t)mt * BM + q * 32;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                const int n0 = nt * BN + h * 32;
+                const int colv = n0 + (lane & 7) * 4;
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool col_ok = p.vecC && colv + 4 <= p.N;
+                if (p.bias != nullptr && col_ok) bb = __ldg(reinterpret_cast<const float4*>(p.bias + colv));
+                mbar_wait(bar(BAR_D_FULL + buf), d_phase, vstatus);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + h * 32);
+                float v[32];
+                {
+                    uint32_t rv[32], rw[32];
+                    tmem_ld32_issue(taddr, rv);
+                    tmem_ld32_issue(taddr + BN, rw);
+                    tmem_ld_wait();
+                    tmem_pin32(rv);
+                    tmem_pin32(rw);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rw[j]), 1.f / 2048.f, __uint_as_float(rv[j]));
+                }
+                // the accumulator buffer is free as soon as it is in registers
+                tc_fence_before();
+                warp_arrive(bar(BAR_D_EMPTY + buf), lane);
+                buf ^= 1;
+                if (buf == 0) d_phase ^= 1;
+
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(T + lane * 32 + 4 * (c ^ (lane & 7))) =
+                        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                __syncwarp();
+                const int g8 = lane & 7;
+                float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+                if (col_ok && m0 + 32 <= p.M) {
+                    float* cp = p.C + (m0 + (lane >> 3)) * p.ldc + colv;
+                    const int64_t step = 4 * p.ldc;
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = rr * 4 + (lane >> 3);
+                        float4 o = *reinterpret_cast<const float4*>(T + r * 32 + 4 * (g8 ^ (r & 7)));
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        if (p.accumulate) {
+                            const float4 old = *reinterpret_cast<const float4*>(cp);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(cp) = o;
+                        s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+                        s2.x = fmaf(o.x, o.x, s2.x); s2.y = fmaf(o.y, o.y, s2.y);
+                        s2.z = fmaf(o.z, o.z, s2.z); s2.w = fmaf(o.w, o.w, s2.w);
+                        cp += step;
+                    }
+                } else if (n0 < p.N) {
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = rr * 4 + (lane >> 3);
+                        const int64_t grow = m0 + r;
+                        if (grow >= p.M) continue;
+                        const float4 t4 = *reinterpret_cast<const float4*>(T + r * 32 + 4 * (g8 ^ (r & 7)));
+                        float ov[4] = {t4.x, t4.y, t4.z, t4.w};
+                        float* cp = p.C + grow * p.ldc + colv;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (colv + j >= p.N) { ov[j] = 0.f; continue; }
+                            if (p.bias != nullptr) ov[j] += __ldg(p.bias + colv + j);
+                            if (p.accumulate) ov[j] += cp[j];
+                            cp[j] = ov[j];
+                        }
+                        s1.x += ov[0]; s1.y += ov[1]; s1.z += ov[2]; s1.w += ov[3];
+                        s2.x = fmaf(ov[0], ov[0], s2.x); s2.y = fmaf(ov[1], ov[1], s2.y);
+                        s2.z = fmaf(ov[2], ov[2], s2.z); s2.w = fmaf(ov[3], ov[3], s2.w);
+                    }
+                }
+                if (want_stats) {
+                    // lanes with equal (lane & 7) hold the same 4 columns for different row groups: fold 4 -> 1
+#pragma unroll
+                    for (int off = 8; off <= 16; off <<= 1) {
+                        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, off); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, off);
+                        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, off); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, off);
+                        s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+                        s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+                    }
+                    if (lane < 8 && n0 < p.N) {
+                        const int64_t prow = (int64_t)mt * 4 + q;
+                        float* ps = p.col_sum + prow * p.N + colv;
+                        float* pq = p.col_sqsum + prow * p.N + colv;
+                        if (colv + 4 <= p.N && (p.N & 3) == 0) {
+                            *reinterpret_cast<float4*>(ps) = s1;
+                            *reinterpret_cast<float4*>(pq) = s2;
+                        } else {
+                            const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
+                            for (int j = 0; j < 4; ++j)
+                                if (colv + j < p.N) { ps[j] = a1[j]; pq[j] = a2[j]; }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// W (weights) -> zero-padded fp16 hi / 2^11-scaled lo, laid out per 64-row column tile as [hi rows ; lo rows] x Kp
+// (one TMA box = one [W_hi ; W_lo] operand tile); clears the status word
+__global__ void presplit_w_kernel(const float* __restrict__ B, int64_t ldb, int transB, int N, int K, int n_tiles, int Kp,
+                                  uint16_t* __restrict__ out, int* status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *status = 0;
+    const int64_t total = (int64_t)n_tiles * BN * Kp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / Kp), k = (int)(i % Kp);
+        float v = 0.f;
+        if (n < N && k < K) v = transB ? __ldg(B + (int64_t)n * ldb + k) : __ldg(B + (int64_t)k * ldb + n);
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn((v - __half2float(hi)) * 2048.f);
+        const int nt = n / BN, r = n % BN;
+        out[((int64_t)nt * 2 * BN + r) * Kp + k] = __half_as_ushort(hi);
+        out[((int64_t)nt * 2 * BN + BN + r) * Kp + k] = __half_as_ushort(lo);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// workspace: 256-byte status block + the pre-split weight tiles
+size_t spgan_gemm_ts_workspace(int N, int K) {
+    const size_t n_tiles = ((size_t)N + BN - 1) / BN, Kp = align_up((size_t)K, BK);
+    return 256 + align_up(n_tiles * 2 * BN * Kp * sizeof(uint16_t), 256);
+}
+
+bool spgan_gemm_ts_supported(int64_t M, int N, int K, const float* A, int64_t lda) {
+    return M >= BM && M < (1LL << 31) && N >= 16 && K >= 16 && K <= MAX_KB * BK && (lda % 4) == 0 &&
+           (reinterpret_cast<uintptr_t>(A) & 15) == 0 && encode_tiled_fn() != nullptr;
+}
+
+int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                  int64_t ldc, const float* bias, int accumulate, const float* a_scale, const float* a_shift, float a_slope,
+                  float* col_sum, float* col_sqsum, void* workspace, cudaStream_t st) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (enc == nullptr) return SPGAN_E_UNSUPPORTED;
+    const int n_tiles = (N + BN - 1) / BN;
+    const int Kp = (int)align_up((size_t)K, BK);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    int* status = reinterpret_cast<int*>(ws);
+    uint16_t* wsplit = reinterpret_cast<uint16_t*>(ws + 256);
+    presplit_w_kernel<<<ew_grid((int64_t)n_tiles * BN * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, n_tiles, Kp, wsplit, status);
+    int rc = spgan_launch_status();
+    if (rc != SPGAN_OK) return rc;
+
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+        const cuuint64_t gstride[1] = {(cuuint64_t)lda * sizeof(float)};
+        const cuuint32_t box[2] = {32, BM};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SPGAN_E_UNSUPPORTED;
+    }
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)n_tiles * 2 * BN};
+        const cuuint64_t gstride[1] = {(cuuint64_t)Kp * sizeof(uint16_t)};
+        const cuuint32_t box[2] = {BK, 2 * BN};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, wsplit, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+            CUDA_SUCCESS)
+            return SPGAN_E_UNSUPPORTED;
+    }
+    TsParams p;
+    p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.accumulate = accumulate;
+    p.a_scale = a_scale; p.a_shift = a_shift; p.a_slope = a_slope;
+    p.col_sum = col_sum; p.col_sqsum = col_sqsum; p.status = status;
+    p.vecC = ((ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+              (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
+    cudaError_t e = cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const int m_tiles = (int)((M + BM - 1) / BM);
+    const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
+    gemm_ts_kernel<<<grid, TS_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+    return spgan_launch_status();
+}

@@ -102,7 +102,8 @@ knn_query_kernel(const float* __restrict__ xq, const float* __restrict__ xsq, in
                 const int jj = (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
                 const float xc_n = s.xs_c[jj];
                 const float m2 = __fmul_rn(-2.0f, acc[a][c]);
-                out[c] = cand_norm_first ? __fadd_rn(__fadd_rn(m2, xc_n), xq_n) : __fadd_rn(__fadd_rn(m2, xq_n), xc_n);
+                const float dq = cand_norm_first ? __fadd_rn(__fadd_rn(m2, xc_n), xq_n) : __fadd_rn(__fadd_rn(m2, xq_n), xc_n);
+                out[c] = WRITE_DIST ? dq : fminf(dq, FLT_MAX);      // selection key: NaN/+inf ordered by index (knn.cu ord_key)
             }
             *reinterpret_cast<float4*>(&s.d[ty * 4 + a][tx * 4]) = make_float4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<float4*>(&s.d[ty * 4 + a][64 + tx * 4]) = make_float4(out[4], out[5], out[6], out[7]);
@@ -157,7 +158,7 @@ knn_query_kernel(const float* __restrict__ xq, const float* __restrict__ xsq, in
     for (int u = 0; u < 8; ++u) {
         const int i = i0 + warp * 8 + u;
         if (lane >= first_rank && lane < K1 && i < Nq)
-            idx[((int64_t)b * Nq + i) * k + (lane - first_rank)] = lj[u];
+            idx[((int64_t)b * Nq + i) * k + (lane - first_rank)] = lj[u] < Nc ? lj[u] : min((int)i, Nc - 1);
     }
 }
 

@@ -130,6 +130,13 @@ struct KnnSmem {
 __device__ __forceinline__ bool lex_less(float d0, int j0, float d1, int j1) {
     return d0 < d1 || (d0 == d1 && j0 < j1);
 }
+// Selection key of a distance.  NaN and +inf (a diverged generator step feeds non-finite features into
+// EdgeConv2's graph) become FLT_MAX: still ordered by candidate index, and still lex_less than the list's
+// (FLT_MAX, 0x7fffffff) sentinel, so every list entry ends up a VALID candidate index as with torch.sort
+// (which puts NaN last).  Finite distances are untouched: one FMNMX per candidate.
+__device__ __forceinline__ float ord_key(float d) { return fminf(d, FLT_MAX); }
+// A list still holding the sentinel (fewer than k+1 candidates) never reaches memory as an index
+__device__ __forceinline__ int valid_nbr(int j, int self, int N) { return j < N ? j : min(self, N - 1); }
 
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_group_kernel(const float* __restrict__ x, const float* __restrict__ xs, int B, int C, int N, int k,
@@ -155,7 +162,7 @@ knn_group_kernel(const float* __restrict__ x, const float* __restrict__ xs, int 
     int lj[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) { ld[u] = FLT_MAX; lj[u] = 0x7fffffff; }
-    // FLT_MAX is a sentinel, not +inf, so that a real +inf distance still sorts deterministically
+    // (FLT_MAX, 0x7fffffff) is the sentinel: every real candidate, ord_key'ed, sorts before it
 
     for (int j0 = 0; j0 < N; j0 += CT) {
         float acc[4][8];
@@ -201,7 +208,7 @@ knn_group_kernel(const float* __restrict__ x, const float* __restrict__ xs, int 
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int jj = (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
-                out[c] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[jj]);
+                out[c] = ord_key(__fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[jj]));
             }
             *reinterpret_cast<float4*>(&s.d[ty * 4 + a][tx * 4]) = make_float4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<float4*>(&s.d[ty * 4 + a][64 + tx * 4]) = make_float4(out[4], out[5], out[6], out[7]);
@@ -248,8 +255,9 @@ knn_group_kernel(const float* __restrict__ x, const float* __restrict__ xs, int 
         const int qq = warp * 8 + u;
         const int i = i0 + qq;
         if (lane >= 1 && lane < K1) {
-            nbr[qq][lane - 1] = lj[u];
-            if (i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = lj[u];
+            const int jn = valid_nbr(lj[u], i, N);
+            nbr[qq][lane - 1] = jn;
+            if (i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = jn;
         }
     }
     if (ee == nullptr) return;
@@ -379,7 +387,7 @@ knn_group_fast_kernel(const float* __restrict__ x, const float* __restrict__ xs,
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int jj = (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
-                out[c] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[tile & 1][jj]);
+                out[c] = ord_key(__fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[tile & 1][jj]));
             }
             *reinterpret_cast<float4*>(&s.d[ty * 4 + a][tx * 4]) = make_float4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<float4*>(&s.d[ty * 4 + a][64 + tx * 4]) = make_float4(out[4], out[5], out[6], out[7]);
@@ -450,8 +458,9 @@ knn_group_fast_kernel(const float* __restrict__ x, const float* __restrict__ xs,
         const int qq = warp * 8 + u;
         const int i = i0 + qq;
         if (lane >= 1 && lane < K1) {
-            nbr[qq][lane - 1] = lj[u];
-            if (i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = lj[u];
+            const int jn = valid_nbr(lj[u], i, N);
+            nbr[qq][lane - 1] = jn;
+            if (i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = jn;
         }
     }
     if (ee == nullptr) return;

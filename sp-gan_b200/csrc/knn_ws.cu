@@ -121,7 +121,7 @@ knn_ws_kernel(const float* __restrict__ x, const float* __restrict__ xs, int C, 
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int jj = (c < 4) ? tx * 4 + c : 64 + tx * 4 + (c - 4);
-                    out[c] = __fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[db][jj]);
+                    out[c] = fminf(__fadd_rn(__fadd_rn(__fmul_rn(-2.0f, acc[a][c]), xq), s.xs_c[db][jj]), FLT_MAX);   // see knn.cu ord_key
                 }
                 *reinterpret_cast<float4*>(&s.d[db][ty * 4 + a][tx * 4]) = make_float4(out[0], out[1], out[2], out[3]);
                 *reinterpret_cast<float4*>(&s.d[db][ty * 4 + a][64 + tx * 4]) = make_float4(out[4], out[5], out[6], out[7]);
@@ -207,7 +207,7 @@ knn_ws_kernel(const float* __restrict__ x, const float* __restrict__ xs, int C, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + sw * 4 + u;
-            if (lane >= 1 && lane < K1 && i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = lj[u];
+            if (lane >= 1 && lane < K1 && i < N) idx[((int64_t)b * N + i) * k + (lane - 1)] = lj[u] < N ? lj[u] : min(i, N - 1);
         }
     }
 }

@@ -4,7 +4,7 @@
 
 namespace tc {
 
-constexpr uint32_t SPIN_LIMIT = 1u << 20;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;      // polls (>= ~60 cycles each): about a second before the guard trips
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -26,14 +26,44 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: returns false if the kernel must abort (deadlock guard; sets *status)
+// Bounded wait (deadlock guard) as ONE asm block: a spin on mbarrier.try_wait with a poll counter.  A timeout is a
+// protocol bug, never a load condition (the limit counts polls of this warp, not wall-clock time): the status word
+// is raised for post-mortem reading and the kernel TRAPS, so the failure surfaces as a CUDA error at the caller's next
+// synchronisation instead of a half-written output tensor flowing on into the step.
+// The function never returns false.  Keeping the loop (and its exit) inside the asm block matters for code
+// generation: a C-level `if (!wait(...)) return;` makes every loop-carried value of the calling role loop
+// control-dependent on a per-thread predicate, and ptxas then treats the operands of UTCHMMA / UTMALDG as
+// divergent (ELECT / R2UR.BROADCAST loops around every instruction).
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* status) {
-    for (uint32_t it = 0; it < SPIN_LIMIT; ++it) {
-        if (mbar_try_wait(bar, parity)) return true;
-        if ((it & 0xfff) == 0xfff && *status != 0) return false;
-    }
-    atomicExch((int*)status, 1);
-    return false;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, %3;\n\t"
+        "@p bra WAIT_LOOP;\n\t"
+        "st.volatile.global.u32 [%2], 1;\n\t"
+        "membar.sys;\n\t"
+        "trap;\n\t"
+        "WAIT_DONE:\n\t"
+        "}"
+        ::"r"(bar), "r"(parity), "l"(status), "r"(SPIN_LIMIT)
+        : "memory");
+    return true;
+}
+// One lane of a CONVERGED warp (elect.sync).  ptxas recognises the pattern: inside `if (elect_one())`, operands that
+// are warp-uniform (kernel parameters, loop counters of warp-uniform loops, the warp index obtained through
+// __shfl_sync) stay in uniform registers and UTCHMMA / UTMALDG issue directly.  Under a plain `if (lane == 0)` every
+// operand is a per-thread value and each UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~160
+// cycles per instruction -- measured: the issuing warp, not the tensor pipe, paced the kernel).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -185,16 +185,23 @@ class Generator(nn.Module):
     def _sphere_graph(self, x, pc_rows, B, N):
         """Neighbour list of EdgeConv1's input.  Without pc_head that input is the sphere itself,
         which train.py generates once and reuses for every step (model.py:231), so the list is
-        cached on (storage, version, shape) of `x` and recomputed whenever `x` changes."""
+        cached on (storage, version, shape) of `x` (with `x` itself kept alive) and recomputed whenever `x` changes."""
         if self.debug_idx is not None and self.debug_idx[0] is not None:
             return self.debug_idx[0]
         knn = lambda: ops.knn_indices(ops.RowsToBcn.apply(pc_rows.detach(), B, pc_rows.shape[1], N), self.nk)
         if not self.cache_sphere_graph or self.use_head:
             return knn()
+        # The entry keeps a strong reference to `x`: while it lives, its storage cannot be freed and handed to a
+        # different point set at the same address, so (address, version counter, geometry) identifies the CONTENT.
+        # (Writes that bypass the version counter -- x.data.copy_() -- are the caller's to announce: set
+        # cache_sphere_graph = False or call invalidate_sphere_graph().)
         key = (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), self.nk, str(x.device))
         if self._graph_cache is None or self._graph_cache[0] != key:
-            self._graph_cache = (key, knn())
+            self._graph_cache = (key, knn(), x)
         return self._graph_cache[1]
+
+    def invalidate_sphere_graph(self):
+        self._graph_cache = None
 
     def _body(self, x, x_rows, style, B, N):
         pc_rows = x_rows

@@ -155,7 +155,13 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
     ws, ws_bytes = None, 0
     tc = engine in (1, 2, 3) and ((not ta and M >= 128 and N >= 16 and K >= 16) or
                                (ta and not tb and bias is None and K >= 4096 and M >= 16 and N >= 16))
-    if tc or (M <= 128 and 256 <= K < 2048):         # tensor-core operands / small-batch split-K partial tiles
+    if tc and ta:
+        # weight-gradient (TN) kernel: converts both operands on the fly, needs only the 256-byte status block
+        # (sizing this from gemm_workspace(N, K) with K = the ROW count asked for gigabytes per backward)
+        ws_bytes = 256
+        ws = torch.empty(64, device=A.device, dtype=torch.float32)
+        LAST_TC_WORKSPACE = ws
+    elif tc or (M <= 128 and 256 <= K < 2048):       # pre-split weight operand / small-batch split-K partial tiles
         ws_bytes = L().gemm_workspace(engine, N, K)
         ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
         if tc:
@@ -164,6 +170,36 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
              bias.data_ptr() if bias is not None else None, int(accumulate), engine,
              ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
     return out
+
+
+def gemm_fused_raw(A, B, bias=None, tb=True, out=None, accumulate=False, a_scale=None, a_shift=None, a_slope=1.0,
+                   want_stats=False):
+    """spgan_gemm_fused: C = lrelu(A * a_scale + a_shift) @ op(B) + bias, optionally with the per-column partial sums
+    of C and C^2 (-> (C, col_sum, col_sqsum)).  Returns None when the shape is outside the fused kernel's envelope."""
+    global LAST_TC_WORKSPACE
+    A, lda = _gemm_operand(A)
+    B, ldb = _gemm_operand(B)
+    M, K = A.shape
+    N = B.shape[0] if tb else B.shape[1]
+    ws_bytes = L().gemm_fused_workspace(M, N, K, A.data_ptr(), lda)
+    if ws_bytes == 0:
+        return None
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
+    LAST_TC_WORKSPACE = ws
+    cs = cq = None
+    if want_stats:
+        rows = L().gemm_fused_stats_rows(M)
+        cs = torch.empty((rows, N), device=A.device, dtype=torch.float32)
+        cq = torch.empty((rows, N), device=A.device, dtype=torch.float32)
+    L().gemm_fused(int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
+                   bias.data_ptr() if bias is not None else None, int(accumulate),
+                   a_scale.data_ptr() if a_scale is not None else None,
+                   a_shift.data_ptr() if a_shift is not None else None, float(a_slope),
+                   cs.data_ptr() if cs is not None else None, cq.data_ptr() if cq is not None else None,
+                   ws.data_ptr(), ws_bytes, _stream())
+    return (out, cs, cq) if want_stats else out
 
 
 class Gemm(Function):

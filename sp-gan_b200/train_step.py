@@ -143,6 +143,11 @@ class WGANGPTrainer:
         self._graph, self._graph_out = g, out
         return self
 
+    def release_graph(self):
+        """Drop the captured step graph and its static buffers (call before destroying the process group: the
+        graph holds the two NCCL all-reduces)."""
+        self._graph, self._graph_out, self._static = None, None, None
+
     def replay(self, z_d=None, z_g=None, real=None, alpha=None):
         """Copy the new inputs into the static buffers (any of them may be omitted = unchanged) and replay the
         captured step.  Returns the static (loss_d, gp, loss_g) device scalars, overwritten by the next replay."""
