@@ -344,6 +344,8 @@ def run_gpu(args, real_stdout):
             a[1] += 1
             if name == "spgan_gemm":
                 a[2] += gemm_flops(ia)
+            elif name == "spgan_gemm_fused":                         # (transB, M, N, K, ...)
+                a[2] += 2.0 * ia[1] * ia[2] * ia[3]
         total = sum(a[0] for a in agg.values())
         if os.environ.get("SPGAN_BENCH_GEMM_TABLE") == "1":        # diagnostic: GEMM time by shape (stderr)
             byshape = {}
@@ -422,56 +424,52 @@ def run_gpu(args, real_stdout):
         def peak_tf():
             return peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s"
-        try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_r1.json")))
-        except OSError:
-            ncu = {}
+        ncu = {}
+        for fn in ("ncu_r1.json", "ncu_r2.json"):                     # later rounds override
+            try:
+                ncu.update(json.load(open(os.path.join(ROOT, "profiles", fn))))
+            except OSError:
+                pass
         # dominant kernel: the tcgen05 GEMM on its biggest shape, the critic's fc2 forward
         # (NT, M = B*N points, N = 1024, K = 256); algorithmic FLOPs per launch = 2*M*N*K
-        dom = [(ia, s_.elapsed_time(e_)) for name, ia, s_, e_ in prof
-               if name == "spgan_gemm" and ia[0] == 0 and ia[1] == 1 and ia[3] == 1024 and ia[4] == 256]
-        g = agg.get("spgan_gemm")
-        if dom and pkg.ops.GEMM_ENGINE in (1, 2):
+        dom = []
+        for name, ia, s_, e_ in prof:
+            if name == "spgan_gemm" and ia[0] == 0 and ia[1] == 1 and ia[3] == 1024 and ia[4] == 256:
+                dom.append((ia[2], s_.elapsed_time(e_)))                    # (transA, transB, M, N, K, ...)
+            elif name == "spgan_gemm_fused" and ia[2] == 1024 and ia[3] == 256:
+                dom.append((ia[1], s_.elapsed_time(e_)))                    # (transB, M, N, K, ...)
+        eng = pkg.ops.GEMM_ENGINE
+        if dom and eng in (1, 2, 3):
             t_ms = sum(t for _, t in dom) / len(dom)
-            fl = gemm_flops(dom[0][0])
+            Mrows = dom[0][0]
+            fl = 2.0 * Mrows * 1024 * 256
             ach = fl / (t_ms / 1e3) / 1e12
-            cap = next((v for kk, v in ncu.items() if kk.startswith("gemm_tc_kernel<128, 1")), {})
-            roofline = {"kernel": "gemm_tc_kernel<128,TF32x3> (tcgen05), critic fc2 forward M=%d N=1024 K=256" % dom[0][0][2],
+            if eng == 3:
+                kname, ckey = "gemm_ts_kernel (tcgen05 TS form, A resident in TMEM, fp16x3 split)", "gemm_ts_kernel"
+                note = ("fp32-faithful fp16x3: 3 tcgen05 kind::f16 MMAs per product (hi*hi, hi*lo, lo*hi), so the "
+                        "attainable fraction of the bf16 peak is 1/3 = 0.333")
+            else:
+                kname, ckey = "gemm_tc_kernel<128,TF32x3> (tcgen05)", "gemm_tc_kernel<128, 1"
+                note = ("fp32-faithful TF32x3: 3 tcgen05 MMAs per product at half the bf16 rate, so the attainable "
+                        "fraction of the bf16 peak is 1/6 = 0.167")
+            cap = next((v for kk, v in ncu.items() if kk.startswith(ckey)), {})
+            roofline = {"kernel": "%s, critic fc2 forward M=%d N=1024 K=256" % (kname, Mrows),
                         "bound": "tensor", "achieved": ach, "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(),
-                        "traffic": cap.get("dram_traffic_bytes"), "traffic_source": "profiles/ncu_r1.json (ncu --set full, same kernel and shape)",
-                        "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 4.0 * dom[0][0][2] * (1024 + 256),
+                        "traffic": cap.get("dram_traffic_bytes"),
+                        "traffic_source": "profiles/ncu_r2.json (ncu --set full, same kernel and shape)" if cap else None,
+                        "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": 4.0 * Mrows * (1024 + 256),
                         "launches_per_step": len(dom), "avg_launch_ms": t_ms,
                         "share_of_step": sum(t for _, t in dom) / total,
                         "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_pct"),
-                        "note": "fp32-faithful TF32x3: 3 tcgen05 MMAs per product at half the bf16 rate, so the attainable "
-                                "fraction of the bf16 peak is 1/6 = 0.167",
-                        "peak_source": peak_src}
-        if roofline is not None and "note" in roofline:
-            # context for the 1/6 remark: the TF32 tensor-pipe rate of this GPU measured the way MEASURED_PEAKS.json
-            # measures bf16 (cuBLAS matmul 8192^3, best of 10) -- a library call used as a yardstick only
-            try:
-                a_ = torch.randn(8192, 8192, device=dev)
-                b_ = torch.randn(8192, 8192, device=dev)
-                old_tf32 = torch.backends.cuda.matmul.allow_tf32
-                torch.backends.cuda.matmul.allow_tf32 = True
-                best = float("inf")
-                for it in range(12):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
-                    if it >= 2:
-                        best = min(best, e0.elapsed_time(e1))
-                torch.backends.cuda.matmul.allow_tf32 = old_tf32
-                tf32_peak = 2.0 * 8192 ** 3 / (best / 1e3) / 1e12
-                roofline["tf32_tflops_cublas_live"] = tf32_peak
-                roofline["frac_of_tf32x3_attainable"] = roofline["achieved"] / (tf32_peak / 3.0)
-                del a_, b_
-            except RuntimeError as exc:                          # yardstick only: never fail the bench on it
-                roofline["tf32_tflops_cublas_live"] = None
-                sys.stderr.write("tf32 yardstick skipped: %s\n" % exc)
-        if g:
+                        "note": note, "peak_source": peak_src, "mma_per_product": 3,
+                        "frac_of_attainable": ach / (peak_tf() / (3.0 if eng == 3 else 6.0))}
+        g, gf = agg.get("spgan_gemm"), agg.get("spgan_gemm_fused")
+        if g or gf:
+            g = [sum(x) for x in zip(g or [0.0, 0, 0.0], gf or [0.0, 0, 0.0])]
             ach = g[2] / (g[0] / 1e3) / 1e12
-            roofline_all = {"kernel": "spgan_gemm, all %d launches of the step" % g[1], "bound": "tensor", "achieved": ach,
-                            "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(), "share_of_step": g[0] / total}
+            roofline_all = {"kernel": "spgan_gemm + spgan_gemm_fused, all %d launches of the step" % g[1], "bound": "tensor",
+                            "achieved": ach, "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(),
+                            "share_of_step": g[0] / total}
             if roofline is None:
                 roofline = dict(roofline_all, traffic=None, peak_source=peak_src)
         else:

@@ -311,7 +311,8 @@ def generator_forward(sd, x, z, opts, training=True, idx1=None, idx2=None, retur
     return (out, x1) if return_x1 else out
 
 
-def generator_interpolate(sd, x, z1, z2, selection, alpha, opts, use_latent=False, training=False):
+def generator_interpolate(sd, x, z1, z2, selection, alpha, opts, use_latent=False, training=False, idx2=None,
+                         return_x1=False):
     """Generator.interpolate (Generator.py:200-261); like the reference it writes into z1."""
     sel = selection == 1
     if not use_latent:
@@ -321,7 +322,8 @@ def generator_interpolate(sd, x, z1, z2, selection, alpha, opts, use_latent=Fals
         s1, s2 = _head(sd, x, z1, opts), _head(sd, x, z2, opts)
         s1[:, :, sel] = s1[:, :, sel] * (1 - alpha) + s2[:, :, sel] * alpha
         style = s1
-    return _generator_body(sd, x, style, opts, training)[0]
+    out, x1 = _generator_body(sd, x, style, opts, training, None, idx2)
+    return (out, x1) if return_x1 else out
 
 
 def discriminator_forward(sd, x, training=True):
@@ -385,17 +387,29 @@ class TrainState:
             self.d[k].requires_grad_(d_flag)
 
 
-def wgan_gp_train_step(st, x, z_d, z_g, real, alpha, lambda_gp=10.0, gamma=1.0, idx2_d=None, idx2_g=None):
+def wgan_gp_train_step(st, x, z_d, z_g, real, alpha, lambda_gp=10.0, gamma=1.0, idx2_d=None, idx2_g=None, trace=None):
     """One iteration of model.py:239-279 with gan='wgan' and GradientPenalty(lambda_gp) added
     to lossD.  x [B,N,3] sphere, z_* [B,N,nz], real [B,3,N], alpha [B,1,1].
     idx2_d / idx2_g optionally pin EdgeConv2's neighbour lists of the two generator forwards
-    (int64 [B, N*k]) for sensitivity studies.  Returns python floats {loss_d, gp, loss_g}."""
+    (int64 [B, N*k]) for sensitivity studies.  Returns python floats {loss_d, gp, loss_g}.
+    `trace` (a dict) receives, per phase p in (d, g): x1_p (EdgeConv2's input), idx2_p (the neighbour list the
+    reference recipe derives from it), fake_p (the generator output) -- what a parity test at full size needs."""
     opts = st.opts
+
+    def g_forward(z, idx2, tag):
+        out, x1 = generator_forward(st.g, x, z, opts, training=True, idx2=idx2, return_x1=True)
+        if trace is not None:
+            with torch.no_grad():
+                trace["x1_" + tag] = x1.detach()
+                trace["idx2_" + tag] = idx2 if idx2 is not None else knn_indices(x1.detach(), opts.nk // 2)
+                trace["fake_" + tag] = out.detach()
+        return out
+
     # ---- D phase ----
     st.set_requires_grad(False, True)
     st.opt_d.zero_grad(set_to_none=True)
     real = real.detach().clone().requires_grad_(True)     # model.py:245 (Variable(..., requires_grad=True))
-    fake = generator_forward(st.g, x, z_d, opts, training=True, idx2=idx2_d).detach()
+    fake = g_forward(z_d, idx2_d, "d").detach()
     d_real = discriminator_forward(st.d, real, True)
     d_fake = discriminator_forward(st.d, fake, True)
     gp = gradient_penalty(lambda t: discriminator_forward(st.d, t, True), real, fake, alpha, lambda_gp, gamma)
@@ -405,7 +419,7 @@ def wgan_gp_train_step(st, x, z_d, z_g, real, alpha, lambda_gp=10.0, gamma=1.0, 
     # ---- G phase ----
     st.set_requires_grad(True, False)
     st.opt_g.zero_grad(set_to_none=True)
-    fake = generator_forward(st.g, x, z_g, opts, training=True, idx2=idx2_g)
+    fake = g_forward(z_g, idx2_g, "g")
     _ = discriminator_forward(st.d, real, True)            # model.py:274 (result unused by wgan gen_loss)
     d_fake = discriminator_forward(st.d, fake, True)
     loss_g = gen_loss_wgan(d_fake)

@@ -297,8 +297,6 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
     }
 }
 
-__global__ void clear_status_kernel(int* status) { *status = 0; }
-
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int BN>
@@ -327,11 +325,11 @@ bool spgan_gemm_tc_tn_supported(int64_t Mo, int No, int64_t K, const float* A, i
     return Mo >= 16 && Mo <= 65536 && No >= 16 && K >= 4096 && (int64_t)Mo * No >= 8192;
 }
 
-// C[Mo,No] (+)= A^T B.  workspace: >= 256 bytes (status word).
+// C[Mo,No] (+)= A^T B.  workspace: >= 256 bytes, zero-initialised by the caller (status word).
 int spgan_gemm_tc_tn(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                      int64_t ldc, int accumulate, void* workspace, cudaStream_t st) {
+    // status word: written only by a pipeline timeout, which also traps (tc_common.cuh); the caller keeps it zeroed
     int* status = reinterpret_cast<int*>(workspace);
-    clear_status_kernel<<<1, 1, 0, st>>>(status);
     if (!accumulate) {
         cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)No * sizeof(float), (size_t)Mo, st);
         if (e != cudaSuccess) return (int)e;

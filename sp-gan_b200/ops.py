@@ -30,11 +30,13 @@ def L():
 # (gradient_penalty.py:31-33, only_inputs=True): parameter gradients are not requested there.
 _INPUT_GRAD_ONLY = False
 
-# engine for spgan_gemm: 0 = fp32 CUDA cores, 1 = tcgen05 tensor cores with the fp32-faithful TF32x3
-# split wherever the shape allows (default), 2 = tcgen05 with the faster bf16x3 split (~2^-16/product).
-# Override with SPGAN_GEMM_ENGINE.  3 = opt-in fp16x3 with scaled residuals (csrc/gemm_tc_f16s.cu, not yet validated).
+# engine for spgan_gemm: 0 = fp32 CUDA cores; 1 = tcgen05 tensor cores with the fp32-faithful TF32x3 split;
+# 2 = tcgen05 with the faster bf16x3 split (~2^-16 per product, not parity-safe); 3 (default) = tcgen05 with the
+# fp16x3 split with scaled residuals (22 significant bits like TF32x3, twice its MMA rate): K <= 256 products run
+# on the TMEM-resident-A kernel (csrc/gemm_ts.cu), the rest on the streaming kernel (csrc/gemm_tc.cu).
+# Override with SPGAN_GEMM_ENGINE.
 import os as _os
-GEMM_ENGINE = int(_os.environ.get("SPGAN_GEMM_ENGINE", "1"))
+GEMM_ENGINE = int(_os.environ.get("SPGAN_GEMM_ENGINE", "3"))
 
 
 # Set by GradientPenalty around netD(interpolates): the critic then records the unfused,
@@ -135,6 +137,7 @@ def _gemm_operand(t):
 # dense contraction
 # =========================================================================================
 LAST_TC_WORKSPACE = None      # most recent tcgen05 workspace (its first int is the kernel's status word)
+_TN_STATUS = {}               # per-device zeroed status block of the weight-gradient kernel
 
 
 def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, engine=None):
@@ -159,7 +162,9 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
         # weight-gradient (TN) kernel: converts both operands on the fly, needs only the 256-byte status block
         # (sizing this from gemm_workspace(N, K) with K = the ROW count asked for gigabytes per backward)
         ws_bytes = 256
-        ws = torch.empty(64, device=A.device, dtype=torch.float32)
+        ws = _TN_STATUS.get(A.device)
+        if ws is None:
+            ws = _TN_STATUS[A.device] = full((64,), 0.0, A.device)       # stays zero: only a (trapping) timeout writes it
         LAST_TC_WORKSPACE = ws
     elif tc or (M <= 128 and 256 <= K < 2048):       # pre-split weight operand / small-batch split-K partial tiles
         ws_bytes = L().gemm_workspace(engine, N, K)

@@ -6,8 +6,13 @@ import torch
 import torch.distributed as dist
 
 
+# Set False to run a trainer as a stand-alone replica inside an initialised process group (no broadcast, no
+# all-reduce): the multi-rank parity test compares the data-parallel step against such replicas.
+SYNC_ENABLED = True
+
+
 def world_size():
-    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    return dist.get_world_size() if SYNC_ENABLED and dist.is_available() and dist.is_initialized() else 1
 
 
 def shard_bounds(total, rank, world):
