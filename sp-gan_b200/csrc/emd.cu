@@ -31,7 +31,7 @@ __device__ __forceinline__ Top2 combine(Top2 a, Top2 b) {
 
 __device__ __forceinline__ float bid_value(float x1, float y1, float z1, float x2, float y2, float z2, float price) {
     const float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
-    const float sq = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float sq = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));      // the reference binary's contraction order
     return __double2float_rn(3.0 - (double)__fsqrt_rn(sq) - (double)price);
 }
 
@@ -160,7 +160,7 @@ emd_auction_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz
     for (int j = tid; j < n; j += EMD_THREADS) {
         const int k = ass[j];
         const float dx = __ldg(p1 + j * 3 + 0) - x2[k], dy = __ldg(p1 + j * 3 + 1) - y2[k], dz = __ldg(p1 + j * 3 + 2) - z2[k];
-        dist[(int64_t)blockIdx.x * n + j] = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        dist[(int64_t)blockIdx.x * n + j] = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
         assignment[(int64_t)blockIdx.x * n + j] = k;
     }
 }

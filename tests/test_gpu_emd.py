@@ -70,3 +70,14 @@ def test_argument_errors():
         e.emdModule()(torch.rand(1, 8000, 3, device="cuda"), torch.rand(1, 8000, 3, device="cuda"), 0.005, 5)
     with pytest.raises(RuntimeError):
         e.emdModule()(torch.rand(1, 64, 3), torch.rand(1, 64, 3), 0.005, 10)       # CPU tensors: no fallback
+
+
+def test_kernel_matches_the_reference_binary_golden():
+    """spgan_emd_auction against dist / assignment of the reference's own kernels (metrics/emd/emd_cuda.cu compiled
+    unmodified, run on a B200: tests/golden/emd_reference.npz), with the deviation rule of tests/test_oracle_emd.py."""
+    from test_oracle_emd import check_against_reference_golden
+
+    def run(a, b, eps, iters):
+        d, s = _emd().emdModule()(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), eps, iters)
+        return d.cpu().numpy(), s.cpu().numpy()
+    check_against_reference_golden(run)

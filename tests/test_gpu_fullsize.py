@@ -304,3 +304,46 @@ def test_knn_with_non_finite_features_returns_valid_indices():
     # finite clouds are untouched by the key mapping
     xf = rng.standard_normal((1, 64, 256)).astype(np.float32)
     assert np.array_equal(pkg.ops.knn_indices(torch.from_numpy(xf).cuda(), 10).cpu().numpy(), knn_ref.knn(xf, 10))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def _pairwise_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import spgan_b200 as pkg
+    try:
+        rng = np.random.default_rng(5)
+        a = torch.from_numpy(R.synthetic_chairs(rng, 37, 512)).cuda()          # 37 rows: ragged over 2 ranks
+        b = torch.from_numpy(R.synthetic_chairs(rng, 20, 512)).cuda()
+        cd_sharded = pkg.pairwise_CD(a, b)
+        cd_local = pkg.pairwise_CD(a, b, shard=False)
+        emd_sharded = pkg.pairwise_EMD(a[:5], b[:4], eps=0.005, iters=50)
+        emd_local = pkg.pairwise_EMD(a[:5], b[:4], eps=0.005, iters=50, shard=False)
+        q.put((rank, bool(torch.equal(cd_sharded, cd_local)), bool(torch.equal(emd_sharded, emd_local)),
+               tuple(cd_sharded.shape), tuple(emd_sharded.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_pairwise_eval_sharded_equals_unsharded():
+    """BASELINE configs[4] shards the S x R matrix by row blocks over the ranks (one all_gather_into_tensor): every
+    rank must end up with the matrix a single GPU computes, bit for bit, also when S does not divide evenly."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairwise_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+    for rank, cd_ok, emd_ok, s1, s2 in res:
+        assert cd_ok and emd_ok, res
+        assert s1 == (37, 20) and s2 == (5, 4)
