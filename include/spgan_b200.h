@@ -165,8 +165,8 @@ int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float *A, 
  *     pro(a)[r,k] = LeakyReLU_{a_slope}(a[r,k] * a_scale[k] + a_shift[k])      (identity when a_scale == NULL)
  * and, when col_sum / col_sqsum are given, row-block partial sums of C and C*C per column:
  *     col_sum[j, n] = sum of C[r, n] over the rows r of block j, j < spgan_gemm_fused_stats_rows(M)
- * (32-row blocks, a fixed order: the result is deterministic; spgan_bn_finalize turns them into the batch mean /
- * variance and the next layer's a_scale / a_shift).  A [M,K] row-major with lda % 4 == 0 and 16-byte aligned;
+ * (one block of rows per (CTA, TMEM lane quarter), accumulated in a fixed order: deterministic; N <= 256;
+ * spgan_bn_finalize turns them into the batch mean / variance and the next layer's a_scale / a_shift).  A [M,K] row-major with lda % 4 == 0 and 16-byte aligned;
  * op(B) as in spgan_gemm.  16 <= K <= 256, M >= 128, N >= 16.  sm_100a kernel: TMA-staged fp32 A tiles, operand
  * split x = hi + 2^-11 lo in fp16 (22 significant bits, 3 tcgen05 MMAs per product), A converted once per
  * 128-row tile into tensor memory and reused for all N/64 column tiles (csrc/gemm_ts.cu).
@@ -224,6 +224,27 @@ int spgan_norm_apply(const float *x, int64_t R, int C, int64_t seg_rows, const f
  * rv = (1-m) rv + m var * R/(R-1); *count += 1 (int64). */
 int spgan_bn_update_running(const float *mean, const float *var, int C, int64_t R, float momentum, float *rm,
                             float *rv, int64_t *count, spgan_stream_t stream);
+/* spgan_colstats over ONE segment (train-mode BatchNorm) with the running-statistics update of
+ * spgan_bn_update_running folded into the finalize pass (one launch fewer per BatchNorm forward). */
+int spgan_colstats_bn(const float *x, int64_t R, int C, float eps, float *mean, float *rstd, float *var,
+                      float momentum, float *rm, float *rv, int64_t *count, void *workspace, spgan_stream_t stream);
+/* The statistics side of spgan_gemm_fused: col_sum / col_sqsum [rows, C] partial sums of a [R, C] GEMM output ->
+ * batch mean, rstd = 1/sqrt(biased var + eps), var; optionally (scale, shift != NULL) the prologue tables of the
+ * consuming spgan_gemm_fused, scale = rstd * gamma, shift = beta - mean * scale (gamma / beta NULL = 1 / 0), and
+ * optionally (rm, rv != NULL) the running-statistics update of nn.BatchNorm.  Partials are combined in double, in
+ * row order (deterministic).  Replaces the separate statistics pass of BatchNorm1d/2d after a 1x1 conv
+ * (Discriminator.py:56-64, Generator.py:59-61). */
+int spgan_bn_finalize(const float *col_sum, const float *col_sqsum, int rows, int C, int64_t R, float eps,
+                      const float *gamma, const float *beta, float *mean, float *rstd, float *var, float *scale,
+                      float *shift, float momentum, float *rm, float *rv, int64_t *count, spgan_stream_t stream);
+/* scale = rstd * gamma, shift = beta - mean * scale from given statistics (eval-mode BatchNorm feeding a fused GEMM). */
+int spgan_bn_tables(const float *mean, const float *rstd, const float *gamma, const float *beta, int C, float *scale,
+                    float *shift, spgan_stream_t stream);
+/* spgan_norm_bwd_reduce over ONE segment that also accumulates the parameter gradients in place:
+ * acc_dbeta[c] += sg[c], acc_dgamma[c] += sgx[c] (either may be NULL). */
+int spgan_norm_bwd_reduce_acc(const float *g, const float *x, float slope, int64_t R, int C, const float *mean,
+                              const float *rstd, const float *gamma, const float *beta, float *sg, float *sgx,
+                              float *acc_dbeta, float *acc_dgamma, void *workspace, spgan_stream_t stream);
 /* First-order backward of y = act(norm(x)*gamma+beta): given g = dL/dy (post-activation) it computes
  * sums sg[s,c] = sum g', sgx[s,c] = sum g' * xhat, where g' = g masked by the LeakyReLU(slope) of the
  * forward (slope 1 = no activation; the mask is recomputed from x, mean, rstd, gamma, beta with the

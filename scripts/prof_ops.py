@@ -25,7 +25,7 @@ del y, pooled
 xw = torch.randn(E, 128, device="cuda", requires_grad=True)
 xy = torch.randn(E, 128, device="cuda", requires_grad=True)
 gw, bw, gy, by = (torch.rand(128, device="cuda").requires_grad_() for _ in range(4))
-prod, *_ = ops.BnActSoftmaxMulKTrain.apply(xw, gw, bw, xy, gy, by, 1e-5, 1e-5, 0.01, k)
+prod = ops.BnActSoftmaxMulKTrain.apply(xw, gw, bw, xy, gy, by, 1e-5, 1e-5, 0.01, k)
 prod.backward(torch.randn_like(prod))
 del xw, xy, prod
 # pairwise Chamfer

@@ -351,7 +351,11 @@ extern "C" size_t spgan_gemm_fused_workspace(int64_t M, int N, int K, const floa
     return spgan_gemm_ts_workspace(N, K);
 }
 
-extern "C" size_t spgan_gemm_fused_stats_rows(int64_t M) { return M <= 0 ? 0 : (size_t)(4 * ((M + 127) / 128)); }
+extern "C" size_t spgan_gemm_fused_stats_rows(int64_t M) {
+    if (M <= 0) return 0;
+    const int64_t tiles = (M + 127) / 128;
+    return (size_t)(4 * (tiles < kNumSMs ? tiles : kNumSMs));           // one partial row per (CTA, lane quarter)
+}
 
 extern "C" int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
                                 int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate,
@@ -360,6 +364,7 @@ extern "C" int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float
     SPGAN_CHECK_ARG(A && B && C && workspace && M >= 1 && N >= 1 && K >= 1);
     SPGAN_CHECK_ARG(lda >= K && ldb >= (transB ? K : N) && ldc >= N);
     SPGAN_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr) && (col_sum == nullptr) == (col_sqsum == nullptr));
+    if (col_sum != nullptr && N > 256) return SPGAN_E_UNSUPPORTED;     // column statistics: up to 4 column tiles
     if (!spgan_gemm_ts_supported(M, N, K, A, lda) || workspace_bytes < spgan_gemm_ts_workspace(N, K) ||
         (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
         return SPGAN_E_UNSUPPORTED;

@@ -52,7 +52,9 @@ constexpr int B_STAGE_BYTES = 2 * BN * 128;       // 16 KB
 constexpr int EPI_BYTES = 8 * 32 * 32 * 4;        // one 32 x 32 fp32 transpose tile per epilogue warp
 constexpr int MAX_KB = 4;                         // K <= 256
 constexpr int TAB_BYTES = 2 * MAX_KB * BK * 4;    // prologue scale / shift tables
-constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + EPI_BYTES + TAB_BYTES + 512 + 1024;
+constexpr int STAT_COLS = 128;                    // per epilogue warp: 32 columns x up to 4 column tiles (N <= 256)
+constexpr int STAT_BYTES = 8 * STAT_COLS * 2 * 4; // running column sums / sums of squares of the CTA's row tiles
+constexpr int SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + EPI_BYTES + TAB_BYTES + STAT_BYTES + 512 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_A0 = 256;
@@ -124,7 +126,7 @@ struct TsParams {
     const float* a_scale;      // prologue tables [K] (both NULL: identity)
     const float* a_shift;
     float a_slope;             // LeakyReLU slope of the prologue (1 = none)
-    float* col_sum;            // epilogue partials [4 * m_tiles, N] (both NULL: none)
+    float* col_sum;            // epilogue partials [4 * gridDim.x, N] (both NULL: none; N <= 256)
     float* col_sqsum;
     int* status;
     int vecC;
@@ -138,7 +140,8 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned char* smB = smA + A_STAGES * A_STAGE_BYTES;
     float* epi_smem = reinterpret_cast<float*>(smB + B_STAGES * B_STAGE_BYTES);
     float* tab = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(epi_smem) + EPI_BYTES);      // scale[256], shift[256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tab) + TAB_BYTES);
+    float* stat = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab) + TAB_BYTES);            // [8][2][STAT_COLS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stat) + STAT_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -329,6 +332,12 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = ew & 3, h = ew >> 2;                 // lane quarter, 32-column half of the 64-column tile
         float* T = epi_smem + ew * (32 * 32);
         const bool want_stats = p.col_sum != nullptr;
+        // running sums of this warp's columns over all of the CTA's row tiles (fixed order: deterministic)
+        float* st1 = stat + ew * 2 * STAT_COLS;
+        float* st2 = st1 + STAT_COLS;
+        if (want_stats)
+            for (int i = lane; i < 2 * STAT_COLS; i += 32) st1[i] = 0.f;
+        __syncwarp();
         int buf = 0;
         uint32_t d_phase = 0;
         for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
@@ -414,21 +423,26 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
                         s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
                     }
-                    if (lane < 8 && n0 < p.N) {
-                        const int64_t prow = (int64_t)mt * 4 + q;
-                        float* ps = p.col_sum + prow * p.N + colv;
-                        float* pq = p.col_sqsum + prow * p.N + colv;
-                        if (colv + 4 <= p.N && (p.N & 3) == 0) {
-                            *reinterpret_cast<float4*>(ps) = s1;
-                            *reinterpret_cast<float4*>(pq) = s2;
-                        } else {
-                            const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
-                            for (int j = 0; j < 4; ++j)
-                                if (colv + j < p.N) { ps[j] = a1[j]; pq[j] = a2[j]; }
-                        }
+                    if (lane < 8) {
+                        float* a1 = st1 + nt * 32 + lane * 4;
+                        float* a2 = st2 + nt * 32 + lane * 4;
+                        a1[0] += s1.x; a1[1] += s1.y; a1[2] += s1.z; a1[3] += s1.w;
+                        a2[0] += s2.x; a2[1] += s2.y; a2[2] += s2.z; a2[3] += s2.w;
                     }
                 }
                 __syncwarp();
+            }
+        }
+        if (want_stats) {
+            // one partial row per (CTA, lane quarter); the two column halves of a tile come from the two warps
+            __syncwarp();
+            const int64_t prow = (int64_t)blockIdx.x * 4 + q;
+            for (int i = lane; i < n_tiles * 32; i += 32) {
+                const int col = (i >> 5) * BN + h * 32 + (i & 31);
+                if (col < p.N) {
+                    p.col_sum[prow * p.N + col] = st1[i];
+                    p.col_sqsum[prow * p.N + col] = st2[i];
+                }
             }
         }
     }

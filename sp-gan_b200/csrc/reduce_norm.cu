@@ -225,15 +225,23 @@ struct StatsOp {
 };
 struct StatsFin {
     const float* x; int C; int64_t seg_rows; float eps; float* mean; float* rstd; float* var;
+    // optional (one segment only): nn.BatchNorm's running-statistics update folded into the finalize
+    float momentum; float unbias; float* rm; float* rv; int64_t* count;
     __device__ void operator()(int64_t seg, int c, const double* s) const {
         const double n = (double)seg_rows;
         const double m1 = s[0] / n;
         double v = s[1] / n - m1 * m1;
         if (v < 0.0) v = 0.0;
         const int64_t o = seg * C + c;
-        mean[o] = (float)((double)x[seg * seg_rows * C + c] + m1);
+        const float m = (float)((double)x[seg * seg_rows * C + c] + m1);
+        mean[o] = m;
         rstd[o] = (float)(1.0 / sqrt(v + (double)eps));
         if (var) var[o] = (float)v;
+        if (rm) {
+            rm[c] = (1.f - momentum) * rm[c] + momentum * m;
+            rv[c] = (1.f - momentum) * rv[c] + momentum * ((float)v * unbias);
+            if (c == 0 && count) *count += 1;
+        }
     }
 };
 // The LeakyReLU mask of the fused BN+activation is recomputed from x (same fma as the forward) instead of
@@ -254,8 +262,12 @@ struct NormBwdOp {
 };
 struct Store2Fin {
     float* a; float* b; int C;
+    // optional (one segment only): accumulate into the parameter gradients (dbeta += sum g', dgamma += sum g' xhat)
+    float* acc_a; float* acc_b;
     __device__ void operator()(int64_t seg, int c, const double* s) const {
         a[seg * C + c] = (float)s[0]; b[seg * C + c] = (float)s[1];
+        if (acc_a) acc_a[c] += (float)s[0];
+        if (acc_b) acc_b[c] += (float)s[1];
     }
 };
 struct DblBwdOp {
@@ -1030,7 +1042,7 @@ extern "C" int spgan_colstats(const float* x, int64_t R, int C, int64_t seg_rows
                               float* rstd, float* var, void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(x && mean && rstd && R >= 1 && C >= 1);
     return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), StatsOp{x, C, seg_rows}, StatsOp4{x, C, seg_rows}, al16(x),
-                            StatsFin{x, C, seg_rows, eps, mean, rstd, var});
+                            StatsFin{x, C, seg_rows, eps, mean, rstd, var, 0.f, 1.f, nullptr, nullptr, nullptr});
 }
 extern "C" int spgan_norm_apply(const float* x, int64_t R, int C, int64_t seg_rows, const float* mean,
                                 const float* rstd, const float* gamma, const float* beta, float slope, float* y,
@@ -1051,13 +1063,84 @@ extern "C" int spgan_bn_update_running(const float* mean, const float* var, int 
     bn_update_running_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(mean, var, C, unbias, momentum, rm, rv, count);
     return spgan_launch_status();
 }
+extern "C" int spgan_colstats_bn(const float* x, int64_t R, int C, float eps, float* mean, float* rstd, float* var,
+                                 float momentum, float* rm, float* rv, int64_t* count, void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(x && mean && rstd && var && rm && rv && R >= 1 && C >= 1);
+    const float unbias = R > 1 ? (float)((double)R / (double)(R - 1)) : 1.f;
+    return run_colreduce<2>(R, C, R, ws, as_stream(s), StatsOp{x, C, R}, StatsOp4{x, C, R}, al16(x),
+                            StatsFin{x, C, R, eps, mean, rstd, var, momentum, unbias, rm, rv, count});
+}
+
+// Column partial sums of a GEMM epilogue (spgan_gemm_fused) -> batch statistics, the consumer's prologue tables and
+// the running-statistics update, one thread per column, partials added in double in row order (deterministic).
+__global__ void bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int rows, int C, double inv_n,
+                                   float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float momentum, float unbias,
+                                   float* rm, float* rv, int64_t* count) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < rows; ++r) { s1 += (double)ps[(int64_t)r * C + c]; s2 += (double)pq[(int64_t)r * C + c]; }
+    const double m = s1 * inv_n;
+    double v = s2 * inv_n - m * m;
+    if (v < 0.0) v = 0.0;
+    const float mf = (float)m, rs = (float)(1.0 / sqrt(v + (double)eps));
+    mean[c] = mf; rstd[c] = rs; var[c] = (float)v;
+    if (scale) {
+        // y = ((x - mean) * rstd) * gamma + beta = x * scale + shift
+        const float sc = rs * (gamma ? gamma[c] : 1.f);
+        scale[c] = sc;
+        shift[c] = fmaf(-mf, sc, beta ? beta[c] : 0.f);
+    }
+    if (rm) {
+        rm[c] = (1.f - momentum) * rm[c] + momentum * mf;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * ((float)v * unbias);
+        if (c == 0 && count) *count += 1;
+    }
+}
+extern "C" int spgan_bn_finalize(const float* col_sum, const float* col_sqsum, int rows, int C, int64_t R, float eps,
+                                 const float* gamma, const float* beta, float* mean, float* rstd, float* var,
+                                 float* scale, float* shift, float momentum, float* rm, float* rv, int64_t* count,
+                                 spgan_stream_t s) {
+    SPGAN_CHECK_ARG(col_sum && col_sqsum && mean && rstd && var && rows >= 1 && C >= 1 && R >= 1);
+    SPGAN_CHECK_ARG((scale == nullptr) == (shift == nullptr) && (rm == nullptr) == (rv == nullptr));
+    const float unbias = R > 1 ? (float)((double)R / (double)(R - 1)) : 1.f;
+    bn_finalize_kernel<<<(C + 63) / 64, 64, 0, as_stream(s)>>>(col_sum, col_sqsum, rows, C, 1.0 / (double)R, eps, gamma, beta,
+                                                               mean, rstd, var, scale, shift, momentum, unbias, rm, rv, count);
+    return spgan_launch_status();
+}
+// (mean, rstd, gamma, beta) -> the prologue tables of spgan_gemm_fused (eval-mode statistics, or a saved batch)
+__global__ void bn_tables_kernel(const float* mean, const float* rstd, const float* gamma, const float* beta, int C,
+                                 float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = rstd[c] * (gamma ? gamma[c] : 1.f);
+    scale[c] = sc;
+    shift[c] = fmaf(-mean[c], sc, beta ? beta[c] : 0.f);
+}
+extern "C" int spgan_bn_tables(const float* mean, const float* rstd, const float* gamma, const float* beta, int C,
+                               float* scale, float* shift, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(mean && rstd && scale && shift && C >= 1);
+    bn_tables_kernel<<<(C + 127) / 128, 128, 0, as_stream(s)>>>(mean, rstd, gamma, beta, C, scale, shift);
+    return spgan_launch_status();
+}
+extern "C" int spgan_norm_bwd_reduce_acc(const float* g, const float* x, float slope, int64_t R, int C, const float* mean,
+                                         const float* rstd, const float* gamma, const float* beta, float* sg, float* sgx,
+                                         float* acc_dbeta, float* acc_dgamma, void* ws, spgan_stream_t s) {
+    SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && R >= 1 && C >= 1);
+    const bool vec = al16(g) && al16(x) && al16(mean) && al16(rstd) && (!gamma || al16(gamma)) && (!beta || al16(beta));
+    return run_colreduce<2>(R, C, R, ws, as_stream(s), NormBwdOp{g, x, slope, C, mean, rstd, gamma, beta},
+                            NormBwdOp4{g, x, slope, C, mean, rstd, gamma, beta}, vec,
+                            Store2Fin{sg, sgx, C, acc_dbeta, acc_dgamma});
+}
 extern "C" int spgan_norm_bwd_reduce(const float* g, const float* x, float slope, int64_t R, int C,
                                      int64_t seg_rows, const float* mean, const float* rstd, const float* gamma,
                                      const float* beta, float* sg, float* sgx, void* ws, spgan_stream_t s) {
     SPGAN_CHECK_ARG(g && x && mean && rstd && sg && sgx && R >= 1 && C >= 1);
     const bool vec = al16(g) && al16(x) && al16(mean) && al16(rstd) && (!gamma || al16(gamma)) && (!beta || al16(beta));
     return run_colreduce<2>(R, C, seg_rows, ws, as_stream(s), NormBwdOp{g, x, slope, C, mean, rstd, gamma, beta},
-                            NormBwdOp4{g, x, slope, C, mean, rstd, gamma, beta}, vec, Store2Fin{sg, sgx, C});
+                            NormBwdOp4{g, x, slope, C, mean, rstd, gamma, beta}, vec, Store2Fin{sg, sgx, C, nullptr, nullptr});
 }
 extern "C" int spgan_norm_bwd_apply(const float* g, const float* x, float slope, int64_t R, int C, int64_t seg_rows,
                                     const float* mean, const float* rstd, const float* gamma, const float* beta,

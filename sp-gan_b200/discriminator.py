@@ -32,10 +32,30 @@ class Discriminator(nn.Module):
     def forward(self, x):
         B, _, N = x.shape
         h = ops.BcnToRows.apply(x)                                               # [B*N, 3]
-        for conv, bn in ((self.mlps[0], self.mlps[1]), (self.mlps[3], self.mlps[4]), (self.mlps[6], self.mlps[7])):
-            h = ops.batch_norm_act(ops.linear(h, conv.weight, conv.bias, zero_bias_grad=ops.feeds_train_bn(bn)), bn, NEG)
+        layers = ((self.mlps[0], self.mlps[1]), (self.mlps[3], self.mlps[4]), (self.mlps[6], self.mlps[7]),
+                  (self.fc2[0], self.fc2[1]))
+        conv0, bn0 = layers[0]
+        y = ops.linear(h, conv0.weight, conv0.bias, zero_bias_grad=ops.feeds_train_bn(bn0))      # K = 3: CUDA cores
+        if all(ops.fused_linear_ok(y.shape[0], layers[i + 1][0].weight, layers[i][1], layers[i + 1][1] if i < 2 else None)
+               for i in range(3)):
+            # conv -> BN -> LeakyReLU -> conv chains as ONE pass per layer: BN + LeakyReLU live in the next GEMM's
+            # operand converter, the batch statistics come out of the producing GEMM's epilogue
+            stats = ops.bn_train_stats(y, bn0)
+            for i in range(3):
+                conv, bn_in, nxt = layers[i + 1][0], layers[i][1], layers[i + 1][1]
+                if i < 2:
+                    y, stats, _ = ops.bn_act_linear(y, stats, bn_in, NEG, conv.weight, conv.bias, next_bn=nxt,
+                                                    zero_bias_grad=ops.feeds_train_bn(nxt))
+                else:
+                    y = ops.bn_act_linear(y, stats, bn_in, NEG, conv.weight, conv.bias,
+                                          zero_bias_grad=ops.feeds_train_bn(nxt))
+            h = y
+        else:
+            h = ops.batch_norm_act(y, bn0, NEG)
+            for conv, bn in layers[1:3]:
+                h = ops.batch_norm_act(ops.linear(h, conv.weight, conv.bias, zero_bias_grad=ops.feeds_train_bn(bn)), bn, NEG)
+            h = ops.linear(h, self.fc2[0].weight, self.fc2[0].bias, zero_bias_grad=ops.feeds_train_bn(self.fc2[1]))
         # fc2 -> BN -> LeakyReLU -> max over points: fused, the [B*N, dim] normalised tensor is never written
-        h = ops.linear(h, self.fc2[0].weight, self.fc2[0].bias, zero_bias_grad=ops.feeds_train_bn(self.fc2[1]))
         h = ops.batch_norm_act_segmax(h, self.fc2[1], NEG, N)                    # [B, dim]
         for i in (0, 2, 4):
             h = ops.LRelu.apply(ops.linear(h, self.mlp[i].weight, self.mlp[i].bias), NEG)

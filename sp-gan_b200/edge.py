@@ -68,9 +68,9 @@ class edgeConv(nn.Module, _KnnMixin):
 
     def forward_rows(self, x_rows, idx32, B, N):
         C, F = self.Fin, self.Fout
-        W = self.conv.conv.weight.view(F, 2 * C)
-        a = ops.linear(x_rows, W[:, :C])                  # centre half, per point
-        d = ops.linear(x_rows, W[:, C:], engine=0)        # difference half, per point (differenced: exact fp32)
+        W = self.conv.conv.weight
+        a = ops.linear(x_rows, W, cols=(0, C))                       # centre half, per point
+        d = ops.linear(x_rows, W, engine=0, cols=(C, 2 * C))         # difference half, per point (differenced: exact fp32)
         y = ops.EdgeCombine.apply(a, d, self.conv.conv.bias, idx32, N, self.k, ops.feeds_train_bn(self.conv.bn))
         y = ops.batch_norm_act(y, self.conv.bn, 0.0)
         return ops.KMax.apply(y, self.k)
@@ -105,16 +105,23 @@ class EdgeBlock(nn.Module, _KnnMixin):
         cx, bx, _ = self.conv_x
         # conv_w on the difference half: W (x_j - x_i) + b == (W x)_j - (W x)_i + b
         p1 = ops.linear(x_rows, cw0.weight, engine=0)          # differenced below: exact fp32 products
-        w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))   # [P*k, F/2]
-        w = ops.batch_norm_act(w, bw0, NEG)
-        w = ops.linear(w, cw1.weight, cw1.bias, zero_bias_grad=ops.feeds_train_bn(bw1))   # [P*k, F], pre-BN
+        w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))   # [P*k, F/2], pre-BN
+        stats_w = None
+        if ops.edge_attention_fusable(bw1, bx, k) and ops.fused_linear_ok(P * k, cw1.weight, bw0, bw1):
+            # BN + LeakyReLU of conv_w[0..2] inside conv_w[3]'s operand converter; the statistics of its output (the
+            # attention logits before their BatchNorm) come out of the same GEMM's epilogue
+            w, st, var_w = ops.bn_act_linear(w, ops.bn_train_stats(w, bw0), bw0, NEG, cw1.weight, cw1.bias, next_bn=bw1,
+                                             zero_bias_grad=ops.feeds_train_bn(bw1))
+            stats_w = (st[0], st[1], var_w)
+        else:
+            w = ops.batch_norm_act(w, bw0, NEG)
+            w = ops.linear(w, cw1.weight, cw1.bias, zero_bias_grad=ops.feeds_train_bn(bw1))   # [P*k, F], pre-BN
         # conv_x on [centre, difference]
-        Wx = cx.weight.view(F, 2 * C)
-        a = ops.linear(x_rows, Wx[:, :C])
-        d = ops.linear(x_rows, Wx[:, C:], engine=0)
+        a = ops.linear(x_rows, cx.weight, cols=(0, C))
+        d = ops.linear(x_rows, cx.weight, engine=0, cols=(C, 2 * C))
         y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k, ops.feeds_train_bn(bx))   # [P*k, F], pre-BN
         # BN + LeakyReLU on both branches, softmax over k, then y * w: one fused pass
-        y = ops.bn_act_softmax_mul_k(w, bw1, y, bx, NEG, k)
+        y = ops.bn_act_softmax_mul_k(w, bw1, y, bx, NEG, k, stats_w)
         # conv_out: kernel [1, k] == one dense contraction over (neighbour, channel)
         Wo = ops.PermuteOCK.apply(self.conv_out.weight)                         # [F, k*F]
         return ops.Gemm.apply(y.view(P, k * F), Wo, self.conv_out.bias, False, True)

@@ -236,8 +236,8 @@ class Generator(nn.Module):
             t = ops.linear(feat, W0, self.tail[0].bias)
         else:
             # tail[0] over cat(global, x2): the global half is constant per cloud -> per-cloud bias
-            gb = ops.linear(g, W0[:, :ng], self.tail[0].bias)                    # [B, 256]
-            t = ops.AddSegVec.apply(ops.linear(x2, W0[:, ng:]), gb, N)
+            gb = ops.linear(g, self.tail[0].weight, self.tail[0].bias, cols=(0, ng))           # [B, 256]
+            t = ops.AddSegVec.apply(ops.linear(x2, self.tail[0].weight, cols=(ng, W0.shape[1])), gb, N)
         t = ops.LRelu.apply(t, NEG)
         t = ops.LRelu.apply(ops.linear(t, self.tail[2].weight, self.tail[2].bias), NEG)
         o = ops.Tanh.apply(ops.linear(t, self.tail[4].weight, self.tail[4].bias))

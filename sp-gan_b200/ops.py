@@ -207,39 +207,70 @@ def gemm_fused_raw(A, B, bias=None, tb=True, out=None, accumulate=False, a_scale
     return (out, cs, cq) if want_stats else out
 
 
+def _wmat(B, cols):
+    """Weight operand as a matrix: [Cout, Cin, 1(, 1)] parameters are viewed as [Cout, K]; `cols` = (c0, c1) selects a
+    column block (the two halves of an EdgeConv weight, the global / local halves of tail[0])."""
+    m = B if B.dim() == 2 else B.reshape(B.shape[0], -1)
+    return m if cols is None else m[:, cols[0]:cols[1]]
+
+
+# Weight gradients of leaf parameters whose .grad already exists (the flat gradient buffer of train_step.FlatAdam)
+# are ACCUMULATED IN PLACE by the weight-gradient GEMM (C += A^T B) and the Function returns None for them: autograd's
+# AccumulateGrad would otherwise launch one at::add per parameter and backward pass (143 per step, 2.4 % of it) and,
+# for column blocks of a weight, a zero-fill + copy for the slice.  Off under create_graph (double backward).
+DIRECT_WEIGHT_GRAD = _os.environ.get("SPGAN_DIRECT_WEIGHT_GRAD", "1") != "0"
+
+
 class Gemm(Function):
     """C = op(A) @ op(B) + bias.  Closed under differentiation (backward = three Gemm/ColSum).
     `engine` (None = module default) pins the arithmetic of the FORWARD product only: the per-point
-    projections that EdgeCombine differences (pn[j] - pn[p]) use engine 0 (exact fp32 FMA chains)."""
+    projections that EdgeCombine differences (pn[j] - pn[p]) use engine 0 (exact fp32 FMA chains).
+    B may be a conv / linear weight of any rank (viewed as [Cout, K]) and `cols` a column block of it."""
 
     @staticmethod
-    def forward(ctx, A, B, bias, ta, tb, engine=None, zero_bias_grad=False):
-        ctx.ta, ctx.tb = ta, tb
+    def forward(ctx, A, B, bias, ta, tb, engine=None, zero_bias_grad=False, cols=None):
+        ctx.ta, ctx.tb, ctx.cols = ta, tb, cols
         ctx.save_for_backward(A, B)
         ctx.has_bias = bias is not None
         ctx.zero_bias_grad = zero_bias_grad
-        return gemm_raw(A, B, bias, ta, tb, engine=engine)
+        return gemm_raw(A, _wmat(B, cols), bias, ta, tb, engine=engine)
 
     @staticmethod
     def backward(ctx, g):
         A, B = ctx.saved_tensors
-        ta, tb = ctx.ta, ctx.tb
+        ta, tb, cols = ctx.ta, ctx.tb, ctx.cols
         dA = dB = db = None
         params_too = not _INPUT_GRAD_ONLY
+        Bm = _wmat(B, cols)
         if ctx.needs_input_grad[0]:
             # C = op(A) op(B):  d op(A) = g op(B)^T
-            dA = Gemm.apply(g, B, None, False, not tb) if not ta else Gemm.apply(B, g, None, tb, True)
+            dA = Gemm.apply(g, Bm, None, False, not tb) if not ta else Gemm.apply(Bm, g, None, tb, True)
         if ctx.needs_input_grad[1] and params_too:
-            dB = Gemm.apply(A, g, None, not ta, False) if not tb else Gemm.apply(g, A, None, True, ta)
-        if ctx.has_bias and ctx.needs_input_grad[2] and params_too:
-            db = full((g.shape[1],), 0.0, g.device) if ctx.zero_bias_grad else ColSum.apply(g, g.shape[0]).view(-1)
-        return dA, dB, db, None, None, None, None
+            if (DIRECT_WEIGHT_GRAD and not torch.is_grad_enabled() and B.is_leaf and B.grad is not None
+                    and B.grad.is_contiguous() and B.grad.dtype == torch.float32 and B.grad.is_cuda):
+                gm = _wmat(B.grad, cols)                     # view of the parameter's gradient (block)
+                if not tb:
+                    gemm_raw(A, g, None, not ta, False, out=gm, accumulate=True)
+                else:
+                    gemm_raw(g, A, None, True, ta, out=gm, accumulate=True)
+            else:
+                dB = Gemm.apply(A, g, None, not ta, False) if not tb else Gemm.apply(g, A, None, True, ta)
+                if cols is not None or B.dim() != 2:         # back to the parameter's own shape
+                    full_ = dB
+                    if cols is not None:
+                        full_ = full((Bm.shape[0], _wmat(B, None).shape[1]), 0.0, dB.device)
+                        full_[:, cols[0]:cols[1]] = dB
+                    dB = full_.reshape(B.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2] and params_too and not ctx.zero_bias_grad:
+            db = ColSum.apply(g, g.shape[0]).view(-1)
+        return dA, dB, db, None, None, None, None, None
 
 
 # A bias added right before a train-mode BatchNorm has an exactly zero gradient (the batch mean removes it; the
 # gradient reaching the conv sums to zero over the batch): the reference computes rounding noise there (~1e-7 of the
 # layer's gradient scale).  With this switch on, those gradients are returned as exact zeros instead of spending a
 # full read of the [rows, C] gradient tensor on the noise (SPGAN_EXACT_ZERO_BIAS_GRAD=0 restores the reduction).
+# "Exact zero" = no gradient is returned for that bias (its .grad keeps the zeros of zero_grad).
 EXACT_ZERO_BIAS_GRAD = _os.environ.get("SPGAN_EXACT_ZERO_BIAS_GRAD", "1") != "0"
 
 
@@ -248,10 +279,10 @@ def feeds_train_bn(bn):
     return EXACT_ZERO_BIAS_GRAD and (bn.training or not bn.track_running_stats)
 
 
-def linear(x, weight, bias=None, engine=None, zero_bias_grad=False):
-    """x [R, Cin] @ weight[Cout, Cin(,1(,1))]^T + bias -- Conv1d(k=1) / Conv2d(1x1) / Linear."""
-    w = weight.reshape(weight.shape[0], -1) if weight.dim() != 2 else weight
-    return Gemm.apply(x, w, bias, False, True, engine, zero_bias_grad)
+def linear(x, weight, bias=None, engine=None, zero_bias_grad=False, cols=None):
+    """x [R, Cin] @ weight[Cout, Cin(,1(,1))]^T + bias -- Conv1d(k=1) / Conv2d(1x1) / Linear; `cols` = (c0, c1)
+    restricts the product to the input-channel block weight[:, c0:c1]."""
+    return Gemm.apply(x, weight, bias, False, True, engine, zero_bias_grad, cols)
 
 
 # =========================================================================================
@@ -510,33 +541,84 @@ class PermuteOCK(Function):
 # =========================================================================================
 # normalisation
 # =========================================================================================
-def col_stats(x, seg_rows, eps):
+def bn_running(bn):
+    """(running_mean, running_var, num_batches_tracked, momentum) when a train-mode forward must advance them."""
+    if bn.training and bn.track_running_stats:
+        if bn.momentum is None:
+            raise NotImplementedError("spgan_b200: BatchNorm(momentum=None) (cumulative average) is not supported; the "
+                                      "reference never uses it (nn.BatchNorm defaults, momentum=0.1)")
+        return (bn.running_mean, bn.running_var, bn.num_batches_tracked, float(bn.momentum))
+    return None
+
+
+def col_stats(x, seg_rows, eps, run=None):
+    """(mean, rstd, biased var) per segment and column; with `run` (bn_running) the BatchNorm running statistics are
+    advanced by the same launch pair (one segment only)."""
     x = _c(_rows2d(x))
     R, C = x.shape
     nseg = R // seg_rows
     mean = torch.empty((nseg, C), device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
     var = torch.empty_like(mean)
-    L().colstats(x.data_ptr(), R, C, seg_rows, eps, mean.data_ptr(), rstd.data_ptr(), var.data_ptr(),
-                 _ws(R, C, seg_rows, 2, x.device).data_ptr(), _stream())
+    ws = _ws(R, C, seg_rows, 2, x.device)
+    if run is not None and seg_rows == R:
+        rm, rv, nbt, mom = run
+        L().colstats_bn(x.data_ptr(), R, C, eps, mean.data_ptr(), rstd.data_ptr(), var.data_ptr(), mom, rm.data_ptr(),
+                        rv.data_ptr(), nbt.data_ptr(), ws.data_ptr(), _stream())
+    else:
+        L().colstats(x.data_ptr(), R, C, seg_rows, eps, mean.data_ptr(), rstd.data_ptr(), var.data_ptr(), ws.data_ptr(),
+                     _stream())
+        if run is not None:
+            rm, rv, nbt, mom = run
+            L().bn_update_running(mean.data_ptr(), var.data_ptr(), mean.numel(), R, mom, rm.data_ptr(), rv.data_ptr(),
+                                  nbt.data_ptr(), _stream())
     return mean, rstd, var
 
 
-def _norm_bwd(g, x, slope, seg_rows, mean, rstd, gamma, beta):
+def _direct_ok(*params):
+    """Parameter gradients may be accumulated in place by the producing kernel (see DIRECT_WEIGHT_GRAD)."""
+    if not DIRECT_WEIGHT_GRAD or torch.is_grad_enabled():
+        return False
+    for p in params:
+        if p is None or not p.is_leaf or not p.requires_grad or p.grad is None or not p.grad.is_contiguous() \
+                or not p.grad.is_cuda or p.grad.dtype != torch.float32:
+            return False
+    return True
+
+
+def _norm_bwd(g, x, slope, seg_rows, mean, rstd, gamma, beta, acc=None):
     """(dx, sum g', sum g' xhat) of y = LeakyReLU_slope(norm(x) * gamma + beta); the activation mask is
-    recomputed from x inside the kernels (slope 1 = no activation)."""
+    recomputed from x inside the kernels (slope 1 = no activation).  acc = (gamma_param, beta_param): their .grad
+    receive dgamma / dbeta in place from the reduction's finalize pass (one segment only)."""
     R, C = x.shape
     nseg = R // seg_rows
     sg = torch.empty((nseg, C), device=x.device, dtype=torch.float32)
     sgx = torch.empty_like(sg)
     gp = gamma.data_ptr() if gamma is not None else None
     bp = beta.data_ptr() if beta is not None else None
-    L().norm_bwd_reduce(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
-                        sg.data_ptr(), sgx.data_ptr(), _ws(R, C, seg_rows, 2, x.device).data_ptr(), _stream())
+    ws = _ws(R, C, seg_rows, 2, x.device)
+    if acc is not None and seg_rows == R:
+        L().norm_bwd_reduce_acc(g.data_ptr(), x.data_ptr(), slope, R, C, mean.data_ptr(), rstd.data_ptr(), gp, bp,
+                                sg.data_ptr(), sgx.data_ptr(), acc[1].grad.data_ptr(), acc[0].grad.data_ptr(),
+                                ws.data_ptr(), _stream())
+    else:
+        L().norm_bwd_reduce(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
+                            sg.data_ptr(), sgx.data_ptr(), ws.data_ptr(), _stream())
     dx = torch.empty_like(x)
     L().norm_bwd_apply(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
                        sg.data_ptr(), sgx.data_ptr(), dx.data_ptr(), _stream())
     return dx, sg, sgx
+
+
+def _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, slope):
+    """Shared first-order backward of the train-mode BatchNorm Functions when no higher-order graph is being built:
+    dgamma / dbeta go straight into the parameters' .grad where possible."""
+    acc = (gamma, beta) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and not _INPUT_GRAD_ONLY
+                            and _direct_ok(gamma, beta)) else None
+    dx, sg, sgx = _norm_bwd(_c(gy), x, slope, x.shape[0], mean, rstd, gamma, beta, acc)
+    if acc is not None or _INPUT_GRAD_ONLY:
+        return dx, None, None
+    return dx, sgx.view(-1), sg.view(-1)
 
 
 class BatchNormTrain(Function):
@@ -544,24 +626,29 @@ class BatchNormTrain(Function):
     Returns (y, batch_mean, biased_batch_var); the last two feed the running-stat update."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps):
+    def forward(ctx, x, gamma, beta, eps, run=None):
         x = _c(_rows2d(x))
         R, C = x.shape
-        mean, rstd, var = col_stats(x, R, eps)
+        mean, rstd, var = col_stats(x, R, eps, run)
         y = torch.empty_like(x)
         L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                        1.0, y.data_ptr(), _stream())
-        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)
         return y, mean, var
 
     @staticmethod
     def backward(ctx, gy, _gm, _gv):
-        x, gamma, mean, rstd = ctx.saved_tensors
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        if gy is None:
+            return None, None, None, None, None
+        if not torch.is_grad_enabled():            # plain first-order pass: no graph of the backward is needed
+            return _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, 1.0) + (None, None)
         dx, dgamma, dbeta = BatchNormTrainBwd.apply(gy, x, gamma, mean, rstd)
         if _INPUT_GRAD_ONLY:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, None
+        return dx, dgamma, dbeta, None, None
 
 
 class BatchNormTrainBwd(Function):
@@ -605,25 +692,30 @@ class BatchNormActTrain2(Function):
     is the closed-form double backward with the activation mask folded in."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, slope):
+    def forward(ctx, x, gamma, beta, eps, slope, run=None):
         x = _c(_rows2d(x))
         R, C = x.shape
-        mean, rstd, var = col_stats(x, R, eps)
+        mean, rstd, var = col_stats(x, R, eps, run)
         y = torch.empty_like(x)
         L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                        slope, y.data_ptr(), _stream())
         ctx.slope = slope
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)
         return y, mean, var
 
     @staticmethod
     def backward(ctx, gy, _gm, _gv):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
+        if gy is None:
+            return None, None, None, None, None, None
+        if not torch.is_grad_enabled():            # the final (first-order) pass over the penalty's graph
+            return _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, ctx.slope) + (None, None, None)
         dx, dgamma, dbeta = BatchNormActTrainBwd2.apply(gy, x, gamma, beta, mean, rstd, ctx.slope)
         if _INPUT_GRAD_ONLY:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, None, None
+        return dx, dgamma, dbeta, None, None, None
 
 
 class BatchNormActTrainBwd2(Function):
@@ -667,25 +759,26 @@ class BatchNormActTrain(Function):
     """Fused train-mode BN + LeakyReLU (slope 0 = ReLU); first-order only (generator path)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, slope):
+    def forward(ctx, x, gamma, beta, eps, slope, run=None):
         x = _c(_rows2d(x))
         R, C = x.shape
-        mean, rstd, var = col_stats(x, R, eps)
+        mean, rstd, var = col_stats(x, R, eps, run)
         y = torch.empty_like(x)
         L().norm_apply(x.data_ptr(), R, C, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                        slope, y.data_ptr(), _stream())
         ctx.slope = slope
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)
         return y, mean, var
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy, _gm, _gv):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
-        gy = _c(gy)
-        dx, sg, sgx = _norm_bwd(gy, x, ctx.slope, x.shape[0], mean, rstd, gamma, beta)
-        return dx, sgx.view(-1), sg.view(-1), None, None
+        if gy is None:
+            return None, None, None, None, None, None
+        return _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, ctx.slope) + (None, None, None)
 
 
 class BatchNormActSegMaxTrain(Function):
@@ -711,12 +804,15 @@ class BatchNormActSegMaxTrain(Function):
         ctx.slope, ctx.seg_rows = slope, seg_rows
         ctx.save_for_backward(x, gamma, beta, mean, rstd, arg)
         ctx.mark_non_differentiable(mean, var)
+        ctx.set_materialize_grads(False)
         return pooled, mean, var
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gp, _gm, _gv):
         x, gamma, beta, mean, rstd, arg = ctx.saved_tensors
+        if gp is None:
+            return None, None, None, None, None, None
         gp = _c(gp)
         R, C = x.shape
         dev = x.device
@@ -730,6 +826,113 @@ class BatchNormActSegMaxTrain(Function):
         return dx, sgx, sg, None, None, None
 
 
+class BnActLinearTrain(Function):
+    """z = LeakyReLU(BatchNorm_train(x_pre)) @ W^T + b in ONE pass over x_pre (spgan_gemm_fused): the normalised,
+    activated tensor never reaches HBM -- it is formed in the GEMM's A-operand converter -- and, with `next_bn`, the
+    batch statistics of z (the next BatchNorm's input) come out of the GEMM's epilogue, so neither the statistics pass
+    nor the apply pass of conv -> BN -> LeakyReLU -> conv chains (Discriminator.py:55-81, Generator.py:56-62) exists.
+    `stats` = (mean, rstd, scale, shift) of x_pre (from a previous BnActLinearTrain or bn_train_stats).
+    Returns (z, mean_z, rstd_z, scale_z, shift_z) (the last four None-like empties without next_bn).
+    Backward (first order): the weight gradient needs the activated input, which is recomputed from x_pre."""
+
+    @staticmethod
+    def forward(ctx, x_pre, mean, rstd, scale, shift, gamma, beta, W, bias, slope, next_bn, zero_bias_grad):
+        x_pre = _c(_rows2d(x_pre))
+        R = x_pre.shape[0]
+        Wm = _wmat(W, None)
+        want = next_bn is not None
+        res = gemm_fused_raw(x_pre, Wm, bias, tb=True, a_scale=scale, a_shift=shift, a_slope=slope, want_stats=want)
+        if res is None:
+            raise RuntimeError("BnActLinearTrain: shape outside spgan_gemm_fused's envelope (caller must check fused_linear_ok)")
+        ctx.slope, ctx.zero_bias_grad, ctx.has_bias = slope, zero_bias_grad, bias is not None
+        ctx.save_for_backward(x_pre, mean, rstd, gamma, beta, W)
+        ctx.set_materialize_grads(False)
+        if not want:
+            return res
+        z, cs, cq = res
+        C2 = z.shape[1]
+        dev = z.device
+        m2 = torch.empty((1, C2), device=dev, dtype=torch.float32)
+        r2, v2, sc2, sh2 = torch.empty_like(m2), torch.empty_like(m2), torch.empty_like(m2), torch.empty_like(m2)
+        run = bn_running(next_bn)
+        L().bn_finalize(cs.data_ptr(), cq.data_ptr(), cs.shape[0], C2, R, float(next_bn.eps), next_bn.weight.data_ptr(),
+                        next_bn.bias.data_ptr(), m2.data_ptr(), r2.data_ptr(), v2.data_ptr(), sc2.data_ptr(), sh2.data_ptr(),
+                        run[3] if run else 0.0, run[0].data_ptr() if run else None, run[1].data_ptr() if run else None,
+                        run[2].data_ptr() if run else None, _stream())
+        ctx.mark_non_differentiable(m2, r2, v2, sc2, sh2)
+        return z, m2, r2, v2, sc2, sh2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz, *_unused):
+        x_pre, mean, rstd, gamma, beta, W = ctx.saved_tensors
+        if gz is None:
+            return (None,) * 12
+        gz = _c(gz)
+        R, K = x_pre.shape
+        Wm = _wmat(W, None)
+        dW = db = dgamma = dbeta = dx = None
+        params_too = not _INPUT_GRAD_ONLY
+        if ctx.needs_input_grad[7] and params_too:
+            a = torch.empty_like(x_pre)                       # recompute the activated input for the weight gradient
+            L().norm_apply(x_pre.data_ptr(), R, K, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                           ctx.slope, a.data_ptr(), _stream())
+            if _direct_ok(W):
+                gemm_raw(gz, a, None, True, False, out=_wmat(W.grad, None), accumulate=True)
+            else:
+                dW = gemm_raw(gz, a, None, True, False).reshape(W.shape)
+            del a
+        if ctx.has_bias and ctx.needs_input_grad[8] and params_too and not ctx.zero_bias_grad:
+            db = ColSum.apply(gz, R).view(-1)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+            ga = gemm_raw(gz, Wm, None, False, False)         # d(activated input)
+            acc = (gamma, beta) if (ctx.needs_input_grad[5] and ctx.needs_input_grad[6] and params_too
+                                    and _direct_ok(gamma, beta)) else None
+            dx, sg, sgx = _norm_bwd(ga, x_pre, ctx.slope, R, mean, rstd, gamma, beta, acc)
+            if acc is None and params_too:
+                dgamma, dbeta = sgx.view(-1), sg.view(-1)
+        return dx, None, None, None, None, dgamma, dbeta, dW, db, None, None, None
+
+
+def fused_linear_ok(R, weight, bn_in, next_bn=None):
+    """Can conv(LeakyReLU(BatchNorm(x))) for a contiguous x [R, K] run as one spgan_gemm_fused launch?  Train-mode
+    statistics with running buffers, first-order graph, the kernel's shape envelope."""
+    if not FUSE_BN_GEMM or _TWICE_DIFFERENTIABLE or GEMM_ENGINE != 3 or not weight.is_cuda:
+        return False
+    if not (bn_in.training and bn_in.track_running_stats and bn_in.momentum is not None):
+        return False
+    if next_bn is not None and not (next_bn.training and next_bn.track_running_stats and next_bn.momentum is not None
+                                    and weight.shape[0] <= 256):
+        return False
+    K = weight[0].numel()
+    return L().gemm_fused_workspace(R, weight.shape[0], K, 256, K) != 0          # (256: any 16-byte aligned address)
+
+
+def bn_train_stats(x_pre, bn):
+    """(mean, rstd, scale, shift) of a pre-normalisation tensor whose producer is not a fused GEMM (a K = 3 conv, the
+    edge gather): the statistics pass (which also advances the running buffers) plus the 1-launch table kernel."""
+    x_pre = _c(_rows2d(x_pre))
+    R, C = x_pre.shape
+    mean, rstd, _ = col_stats(x_pre.detach(), R, bn.eps, bn_running(bn))
+    scale, shift = torch.empty_like(mean), torch.empty_like(mean)
+    L().bn_tables(mean.data_ptr(), rstd.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(), C, scale.data_ptr(),
+                  shift.data_ptr(), _stream())
+    return mean, rstd, scale, shift
+
+
+def bn_act_linear(x_pre, stats, bn_in, slope, weight, bias, next_bn=None, zero_bias_grad=False):
+    """conv(LeakyReLU_slope(bn_in(x_pre))) fused (see BnActLinearTrain); stats = (mean, rstd, scale, shift) of x_pre.
+    -> z, or (z, (mean, rstd, scale, shift), var) of z when next_bn is given."""
+    mean, rstd, scale, shift = stats
+    out = BnActLinearTrain.apply(x_pre, mean, rstd, scale, shift, bn_in.weight, bn_in.bias, weight, bias, slope, next_bn,
+                                 zero_bias_grad)
+    if next_bn is None:
+        return out
+    z, m2, r2, v2, sc2, sh2 = out
+    return z, (m2, r2, sc2, sh2), v2
+
+
+FUSE_BN_GEMM = _os.environ.get("SPGAN_FUSE_BN_GEMM", "1") != "0"
 FUSE_BN_POOL = _os.environ.get("SPGAN_FUSE_BN_POOL", "1") != "0"
 
 
@@ -838,25 +1041,23 @@ FUSE_BN_ACT_2ND = _os.environ.get("SPGAN_FUSE_BN_ACT_2ND", "1") != "0"
 def batch_norm_act(y, bn, slope):
     """nn.BatchNorm{1,2}d (+ LeakyReLU(slope); slope 1 = none) on rows [R, C], honouring bn.training and
     updating the running statistics like the reference modules do in train mode."""
-    R = y.shape[0]
     if bn.training or not bn.track_running_stats:
+        run = bn_running(bn)                # the statistics pass also advances the running buffers
         if _TWICE_DIFFERENTIABLE and FUSE_BN_ACT_2ND and slope != 1.0 and y.shape[1] % 4 == 0:
-            z, mean, var = BatchNormActTrain2.apply(y, bn.weight, bn.bias, bn.eps, slope)
+            z, mean, var = BatchNormActTrain2.apply(y, bn.weight, bn.bias, bn.eps, slope, run)
         elif _TWICE_DIFFERENTIABLE:
-            z, mean, var = BatchNormTrain.apply(y, bn.weight, bn.bias, bn.eps)
+            z, mean, var = BatchNormTrain.apply(y, bn.weight, bn.bias, bn.eps, run)
             if slope != 1.0:
                 z = LRelu.apply(z, slope)
         else:
-            z, mean, var = BatchNormActTrain.apply(y, bn.weight, bn.bias, bn.eps, slope)
-        if bn.track_running_stats and bn.training:
-            bn_update_running(mean, var, R, bn)
+            z, mean, var = BatchNormActTrain.apply(y, bn.weight, bn.bias, bn.eps, slope, run)
         return z
     return NormAffineEval.apply(y, bn.weight, bn.bias, bn.running_mean, rsqrt_eps(bn.running_var, bn.eps), slope)
 
 
 def bn_update_running(mean, var, R, bn):
     """Side effect of a train-mode forward on nn.BatchNorm buffers (momentum, unbiased var, count)."""
-    m = bn.momentum if bn.momentum is not None else 0.1
+    m = bn_running(bn)[3]
     L().bn_update_running(mean.data_ptr(), var.data_ptr(), mean.numel(), R, float(m), bn.running_mean.data_ptr(),
                           bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(), _stream())
 
@@ -1036,14 +1237,19 @@ class BnActSoftmaxMulKTrain(Function):
     """prod = lrelu(bn_y(xy)) * softmax_k(lrelu(bn_w(xw))) with both train-mode BatchNorm2d + LeakyReLU
     applications folded into the loads (EdgeBlock, Generator.py:78-82): the two normalised [E, C] tensors are
     never written (4 fewer full-tensor passes per EdgeBlock forward).  xw, xy are the PRE-normalisation
-    tensors [P*k, C].  Returns (prod, mean_w, var_w, mean_y, var_y).  First-order only."""
+    tensors [P*k, C].  `stats_w`: (mean, rstd, var) of xw when the producing GEMM's epilogue already has them.
+    Returns prod.  First-order only."""
 
     @staticmethod
-    def forward(ctx, xw, gamma_w, beta_w, xy, gamma_y, beta_y, eps_w, eps_y, slope, k):
+    def forward(ctx, xw, gamma_w, beta_w, xy, gamma_y, beta_y, eps_w, eps_y, slope, k, run_w=None, run_y=None,
+                stats_w=None):
         xw, xy = _c(_rows2d(xw)), _c(_rows2d(xy))
         E, C = xw.shape
-        mean_w, rstd_w, var_w = col_stats(xw, E, eps_w)
-        mean_y, rstd_y, var_y = col_stats(xy, E, eps_y)
+        if stats_w is not None:           # (mean, rstd, var) from the producing GEMM's epilogue (running stats done there)
+            mean_w, rstd_w, var_w = stats_w
+        else:
+            mean_w, rstd_w, var_w = col_stats(xw, E, eps_w, run_w)
+        mean_y, rstd_y, var_y = col_stats(xy, E, eps_y, run_y)
         w = torch.empty_like(xw)
         prod = torch.empty_like(xw)
         L().bn_softmax_mul_k(xw.data_ptr(), xy.data_ptr(), E // k, k, C, mean_w.data_ptr(), rstd_w.data_ptr(),
@@ -1051,13 +1257,15 @@ class BnActSoftmaxMulKTrain(Function):
                              gamma_y.data_ptr(), beta_y.data_ptr(), slope, w.data_ptr(), prod.data_ptr(), _stream())
         ctx.k, ctx.slope = k, slope
         ctx.save_for_backward(xw, xy, w, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y)
-        ctx.mark_non_differentiable(mean_w, var_w, mean_y, var_y)
-        return prod, mean_w, var_w, mean_y, var_y
+        ctx.set_materialize_grads(False)
+        return prod
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g, *_unused):
+    def backward(ctx, g):
         xw, xy, w, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y = ctx.saved_tensors
+        if g is None:
+            return (None,) * 13
         g = _c(g)
         E, C = xw.shape
         dwa = torch.empty_like(xw)
@@ -1065,26 +1273,30 @@ class BnActSoftmaxMulKTrain(Function):
         L().bn_softmax_mul_k_bwd(g.data_ptr(), xy.data_ptr(), w.data_ptr(), E // ctx.k, ctx.k, C, mean_y.data_ptr(),
                                  rstd_y.data_ptr(), gamma_y.data_ptr(), beta_y.data_ptr(), ctx.slope, dwa.data_ptr(),
                                  dya.data_ptr(), _stream())
-        dxw, sg_w, sgx_w = _norm_bwd(dwa, xw, ctx.slope, E, mean_w, rstd_w, gamma_w, beta_w)
+        acc_w = (gamma_w, beta_w) if ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and _direct_ok(gamma_w, beta_w) else None
+        acc_y = (gamma_y, beta_y) if ctx.needs_input_grad[4] and ctx.needs_input_grad[5] and _direct_ok(gamma_y, beta_y) else None
+        dxw, sg_w, sgx_w = _norm_bwd(dwa, xw, ctx.slope, E, mean_w, rstd_w, gamma_w, beta_w, acc_w)
         del dwa
-        dxy, sg_y, sgx_y = _norm_bwd(dya, xy, ctx.slope, E, mean_y, rstd_y, gamma_y, beta_y)
-        return dxw, sgx_w.view(-1), sg_w.view(-1), dxy, sgx_y.view(-1), sg_y.view(-1), None, None, None, None
+        dxy, sg_y, sgx_y = _norm_bwd(dya, xy, ctx.slope, E, mean_y, rstd_y, gamma_y, beta_y, acc_y)
+        return (dxw, None if acc_w else sgx_w.view(-1), None if acc_w else sg_w.view(-1),
+                dxy, None if acc_y else sgx_y.view(-1), None if acc_y else sg_y.view(-1)) + (None,) * 7
 
 
 FUSE_EDGE_ATTENTION = _os.environ.get("SPGAN_FUSE_EDGE_ATTENTION", "1") != "0"
 
 
-def bn_act_softmax_mul_k(xw, bn_w, xy, bn_y, slope, k):
+def edge_attention_fusable(bn_w, bn_y, k):
+    return (FUSE_EDGE_ATTENTION and k <= 16 and bn_w.training and bn_y.training and bn_w.track_running_stats
+            and bn_y.track_running_stats and not _TWICE_DIFFERENTIABLE)
+
+
+def bn_act_softmax_mul_k(xw, bn_w, xy, bn_y, slope, k, stats_w=None):
     """EdgeBlock's y * softmax_k(w) over the two BatchNorm2d + LeakyReLU branches (Generator.py:78-82), fused on
     the train-mode path; eval mode runs the generic chain."""
-    E = xw.shape[0]
-    if (FUSE_EDGE_ATTENTION and k <= 16 and bn_w.training and bn_y.training and bn_w.track_running_stats
-            and bn_y.track_running_stats and not _TWICE_DIFFERENTIABLE):
-        prod, mean_w, var_w, mean_y, var_y = BnActSoftmaxMulKTrain.apply(
-            xw, bn_w.weight, bn_w.bias, xy, bn_y.weight, bn_y.bias, bn_w.eps, bn_y.eps, slope, k)
-        bn_update_running(mean_w, var_w, E, bn_w)
-        bn_update_running(mean_y, var_y, E, bn_y)
-        return prod
+    if edge_attention_fusable(bn_w, bn_y, k):
+        return BnActSoftmaxMulKTrain.apply(xw, bn_w.weight, bn_w.bias, xy, bn_y.weight, bn_y.bias, bn_w.eps, bn_y.eps,
+                                           slope, k, None if stats_w is not None else bn_running(bn_w),
+                                           bn_running(bn_y), stats_w)
     return SoftmaxMulK.apply(batch_norm_act(xw, bn_w, slope), batch_norm_act(xy, bn_y, slope), k)
 
 
@@ -1148,7 +1360,7 @@ class EdgeCombine(Function):
                              dpn.data_ptr(), _stream())
         db = None
         if has_bias and ctx.needs_input_grad[2]:
-            db = full((C,), 0.0, g.device) if ctx.zero_bias_grad else ColSum.apply(g, g.shape[0]).view(-1)
+            db = None if ctx.zero_bias_grad else ColSum.apply(g, g.shape[0]).view(-1)
         return dpc, dpn, db, None, None, None, None
 
 

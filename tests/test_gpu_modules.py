@@ -38,8 +38,12 @@ def _check_grads(module, g, prefix="grad.", tol=TOL, max_tol=None):
         if prefix + k not in g:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
-        assert p.grad is not None, k
         ref = g[prefix + k]
+        if p.grad is None:
+            # a bias feeding a train-mode BatchNorm: mathematically zero gradient, the product returns none at all
+            assert float(np.abs(ref).max()) < 1e-4 * scale, (k, "missing gradient")
+            n += 1
+            continue
         if float(np.abs(ref).max()) < 1e-4 * scale:
             got = pack_like_golden(p.grad)
             assert float(np.abs(got - ref).max()) <= tol * 1e-2 * scale, (k, "noise-level gradient too large")
