@@ -155,6 +155,11 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  * The first int of the workspace is a status word: non-zero after completion means the kernel
  * aborted on an internal pipeline timeout (never expected; checked by the tests). */
 size_t spgan_gemm_workspace(int engine, int N, int K);
+/* Workspace of the weight-gradient form (transA = 1, transB = 0: C[Mo,No] = A^T B, K = rows) on engine 3: a 256-byte
+ * status block plus the split-K partial tiles [k_chunks, Mo, No] that csrc/gemm_wg.cu adds up in a fixed order
+ * (deterministic; the engine-1 kernel, taken for shapes / alignments outside gemm_wg.cu's envelope or when the
+ * workspace is smaller, flushes with atomics).  The status word is written only by a pipeline timeout, which traps. */
+size_t spgan_gemm_wgrad_workspace(int64_t Mo, int No, int64_t K);
 int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float *A, int64_t lda, const float *B,
                int64_t ldb, float *C, int64_t ldc, const float *bias, int accumulate, int engine, void *workspace,
                size_t workspace_bytes, spgan_stream_t stream);

@@ -295,6 +295,14 @@ bool spgan_gemm_ts_supported(int64_t M, int N, int K, const float* A, int64_t ld
 int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                   int64_t ldc, const float* bias, int accumulate, const float* a_scale, const float* a_shift, float a_slope,
                   float* col_sum, float* col_sqsum, void* workspace, cudaStream_t st);
+bool spgan_gemm_wg_supported(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb);
+size_t spgan_gemm_wg_workspace(int64_t Mo, int No, int64_t K);
+int spgan_gemm_wg(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                  int64_t ldc, int accumulate, void* workspace, cudaStream_t st);
+static bool wg_enabled() {
+    static const bool on = [] { const char* e = getenv("SPGAN_WG"); return !(e && e[0] == '0'); }();
+    return on;
+}
 static bool ts_enabled() {
     static const bool on = [] { const char* e = getenv("SPGAN_TS"); return !(e && e[0] == '0'); }();
     return on;
@@ -333,8 +341,14 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
         workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
         return spgan_gemm_tc(engine - 1, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
                              as_stream(stream));
-    if (engine == 3) engine = 1;          // weight gradients: the TF32x3 transposing kernel for every tensor engine
-    // weight gradients: C[M,N] = A^T B with A [K,M], B [K,N], K = #points (TF32x3 for both tensor engines)
+    // weight gradients: C[M,N] = A^T B with A [K,M], B [K,N], K = #points.  Engine 3: the TMA / TMEM kernel with
+    // deterministic split-K partials (gemm_wg.cu) when the caller's workspace holds them; SPGAN_WG=0 disables it
+    if (engine == 3 && workspace != nullptr && transA && !transB && bias == nullptr && wg_enabled() &&
+        (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && spgan_gemm_wg_supported(M, N, K, A, lda, B, ldb) &&
+        workspace_bytes >= spgan_gemm_wg_workspace(M, N, K))
+        return spgan_gemm_wg(M, N, K, A, lda, B, ldb, C, ldc, accumulate, workspace, as_stream(stream));
+    if (engine == 3) engine = 1;          // otherwise the TF32x3 transposing kernel for every tensor engine
+    // weight gradients, first generation (TF32x3, atomic flush)
     if ((engine == 1 || engine == 2) && workspace != nullptr && workspace_bytes >= 256 && transA && !transB &&
         bias == nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
         spgan_gemm_tc_tn_supported(M, N, K, A, lda, B, ldb))
@@ -370,4 +384,9 @@ extern "C" int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float
         return SPGAN_E_UNSUPPORTED;
     return spgan_gemm_ts(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, a_scale, a_shift, a_slope, col_sum,
                          col_sqsum, workspace, as_stream(stream));
+}
+
+extern "C" size_t spgan_gemm_wgrad_workspace(int64_t Mo, int No, int64_t K) {
+    if (Mo < 1 || No < 1 || K < 1) return 256;
+    return spgan_gemm_wg_workspace(Mo, No, K);
 }

@@ -161,10 +161,15 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
     if tc and ta:
         # weight-gradient (TN) kernel: converts both operands on the fly, needs only the 256-byte status block
         # (sizing this from gemm_workspace(N, K) with K = the ROW count asked for gigabytes per backward)
-        ws_bytes = 256
-        ws = _TN_STATUS.get(A.device)
-        if ws is None:
-            ws = _TN_STATUS[A.device] = full((64,), 0.0, A.device)       # stays zero: only a (trapping) timeout writes it
+        if engine == 3:
+            # status block + the deterministic split-K partial tiles of csrc/gemm_wg.cu (a few MB)
+            ws_bytes = L().gemm_wgrad_workspace(M, N, K)
+            ws = torch.empty(ws_bytes // 4, device=A.device, dtype=torch.float32)
+        else:
+            ws_bytes = 256
+            ws = _TN_STATUS.get(A.device)
+            if ws is None:
+                ws = _TN_STATUS[A.device] = full((64,), 0.0, A.device)   # stays zero: only a (trapping) timeout writes it
         LAST_TC_WORKSPACE = ws
     elif tc or (M <= 128 and 256 <= K < 2048):       # pre-split weight operand / small-batch split-K partial tiles
         ws_bytes = L().gemm_workspace(engine, N, K)

@@ -138,3 +138,29 @@ def test_bn_act_linear_chain_matches_unfused_modules():
         assert rel_err(a.running_mean.cpu().numpy(), b.running_mean.numpy())[1] < 1e-5
         assert rel_err(a.running_var.cpu().numpy(), b.running_var.numpy())[1] < 1e-5
         assert int(a.num_batches_tracked) == 1
+
+
+WG_SHAPES = [(1024, 256, 131072), (256, 128, 131072), (128, 1280, 40000), (128, 64, 400000), (64, 32, 50000),
+             (72, 500, 9004), (100, 36, 5000), (64, 640, 20000), (16, 1024, 4096), (130, 70, 8200)]
+
+
+@pytest.mark.parametrize("Mo,No,K", WG_SHAPES)
+def test_wgrad_engine3_matches_fp64_and_is_deterministic(Mo, No, K):
+    """Weight-gradient form C = A^T B on csrc/gemm_wg.cu (TMA-staged fp32 tiles, column-wise converters, A in TMEM,
+    split-K partials added in a fixed order): fp64 parity, bit-identical repeats, C += and strided outputs."""
+    ops = _ops()
+    A, B = _rnd(K, Mo, seed=11).cuda(), _rnd(K, No, seed=12).cuda()
+    ref = A.double().cpu().t() @ B.double().cpu()
+    out = ops.gemm_raw(A, B, None, True, False, engine=3)
+    emax, el2 = rel_err(out.cpu().numpy(), ref.numpy())
+    # accumulation chains of 4096 rows in the truncating fp32 TMEM accumulator: ~1.2e-9 relative per k
+    assert emax < 4e-5 and el2 < 8e-6, (emax, el2)
+    out2 = ops.gemm_raw(A, B, None, True, False, engine=3)
+    if Mo % 4 == 0 and No % 4 == 0 and Mo >= 16 and No >= 16:       # inside gemm_wg.cu's envelope: deterministic
+        assert torch.equal(out, out2)
+    # accumulate into a column block of a wider matrix (the in-place parameter-gradient path of ops.Gemm.backward)
+    wide = torch.ones(Mo, No + 8, device="cuda")
+    ops.gemm_raw(A, B, None, True, False, out=wide[:, 4:4 + No], accumulate=True, engine=3)
+    emax, el2 = rel_err((wide[:, 4:4 + No] - 1).cpu().numpy(), ref.numpy())
+    assert emax < 8e-5 and el2 < 1.6e-5, (emax, el2)
+    assert float(wide[:, :4].min()) == 1.0 and float(wide[:, 4 + No:].max()) == 1.0
