@@ -57,6 +57,21 @@ const char *spgan_error_string(int code);
  * 4-way interleaved order ATen applies to its vector tail. */
 int spgan_sqnorm(const float *x_bcn, int B, int C, int N, int main_cols, float *xs, spgan_stream_t stream);
 
+/* The same squared norms (same reduction orders) for point-major rows [B*N, C]. */
+int spgan_sqnorm_pm(const float *x_rows, int B, int C, int N, int main_cols, float *xs, spgan_stream_t stream);
+
+/* Neighbour lists of point-major rows [B*N, C] by tensor-core filter + exact refine (csrc/knn_tc.cu): approximate
+ * distances (tcgen05, fp16x3 split, A operand in tensor memory) select, for every query, every candidate within a
+ * proven error margin of its (k+1)-th smallest approximate distance; the reference's exact fp32 recipe then ranks only
+ * those (a handful per query) by (dist, index).  Bit-identical to spgan_knn_group on the same points; queries whose
+ * candidate list overflows or comes up short (duplicate-heavy or non-finite clouds) are ranked by an exact scan.
+ * xs from spgan_sqnorm_pm.  N % 128 == 0, 16 <= C <= 256, C % 4 == 0, k <= 15.
+ * spgan_knn_rows_workspace returns the workspace bytes (256-byte aligned buffer) or 0 when the shape is outside the
+ * envelope (the caller then uses spgan_knn_group).  workspace[1] (int32) counts the queries ranked by the exact scan. */
+size_t spgan_knn_rows_workspace(int B, int C, int N, int k);
+int spgan_knn_rows(const float *x_rows, const float *xs, int B, int C, int N, int k, int32_t *idx, void *workspace,
+                   size_t workspace_bytes, spgan_stream_t stream);
+
 /* idx[b,n,r] = rank r+1 of row n of dist (rank 0 dropped), int32 [B,N,k]; 1 <= k <= 31, k < N.
  * If ee != NULL also writes the grouped edge features ee[B,2C,N,k] (first C channels the
  * centre point, last C neighbour - centre; modules.py:717-720) in the same kernel. */

@@ -8,5 +8,5 @@ M, N, K = (int(v) for v in sys.argv[1:4])
 A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); out = torch.empty(M, N, device="cuda")
 bias = torch.randn(N, device="cuda")
 for _ in range(3):
-    pkg.ops.gemm_raw(A, B, bias, False, True, out=out, engine=1)
+    pkg.ops.gemm_raw(A, B, bias, False, True, out=out)
 torch.cuda.synchronize()

@@ -48,7 +48,7 @@ class SpganError(RuntimeError):
 
 
 # kernel launches behind one C-ABI call (1 unless listed)
-_LAUNCHES = {"spgan_colstats_bn": 2, "spgan_norm_bwd_reduce_acc": 2, "spgan_gemm_fused": 2, "spgan_colsum": 2, "spgan_coldot": 2, "spgan_colstats": 2, "spgan_norm_bwd_reduce": 2,
+_LAUNCHES = {"spgan_knn_rows": 3, "spgan_colstats_bn": 2, "spgan_norm_bwd_reduce_acc": 2, "spgan_gemm_fused": 2, "spgan_colsum": 2, "spgan_coldot": 2, "spgan_colstats": 2, "spgan_norm_bwd_reduce": 2,
              "spgan_bn_dbl_bwd_reduce": 2, "spgan_bn_dbl_bwd_apply": 2, "spgan_gp_penalty": 2,
              "spgan_bn_pool_fwd": 2, "spgan_bn_pool_bwd": 2, "spgan_adam_step_dev": 2}
 

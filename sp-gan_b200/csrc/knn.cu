@@ -507,6 +507,22 @@ __global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, i
 
 }  // namespace
 
+// the same reduction orders for point-major rows [B*N, C] (channel stride 1)
+__global__ void sqnorm_pm_kernel(const float* __restrict__ rows, int B, int C, int N, int main_cols, float* __restrict__ xs) {
+    const int64_t total = (int64_t)B * N;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(t % N);
+        const float* col = rows + t * C;
+        xs[t] = (n < main_cols) ? sqnorm_cascade(col, C, 1) : sqnorm_ilp4(col, C, 1);
+    }
+}
+extern "C" int spgan_sqnorm_pm(const float* rows, int B, int C, int N, int main_cols, float* xs, spgan_stream_t stream) {
+    SPGAN_CHECK_ARG(rows && xs && B >= 1 && C >= 1 && N >= 1);
+    if (main_cols < 0) main_cols = (N / 32) * 32;
+    const int64_t total = (int64_t)B * N;
+    sqnorm_pm_kernel<<<ew_grid(total, 128), 128, 0, as_stream(stream)>>>(rows, B, C, N, main_cols, xs);
+    return spgan_launch_status();
+}
 extern "C" int spgan_sqnorm(const float* x, int B, int C, int N, int main_cols, float* xs, spgan_stream_t stream) {
     SPGAN_CHECK_ARG(x && xs && B >= 0 && C >= 1 && N >= 1);
     if (B == 0) return SPGAN_OK;

@@ -217,7 +217,7 @@ class Generator(nn.Module):
         if self.debug_idx is not None and self.debug_idx[1] is not None:
             idx2 = self.debug_idx[1]
         else:
-            idx2 = ops.knn_indices(ops.RowsToBcn.apply(x1.detach(), B, x1.shape[1], N), self.nk)
+            idx2 = ops.knn_indices_rows(x1, B, N, self.nk)       # point-major: no [B,C,N] transpose of the features
         x2 = self.EdgeConv2.forward_rows(x1, idx2, B, N)
         x2 = self.adain2.forward_rows(ops.LRelu.apply(x2, NEG_2), style, N)
         self._last_x1 = x1.detach()

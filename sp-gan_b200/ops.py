@@ -1386,6 +1386,29 @@ def knn_indices(x_bcn, k, want_ee=False, main_cols=-1):
     return (idx, ee) if want_ee else idx
 
 
+KNN_TC = _os.environ.get("SPGAN_KNN_TC", "1") != "0"
+LAST_KNN_WORKSPACE = None         # int32 view: [1] = queries of the last spgan_knn_rows call ranked by the exact scan
+
+
+def knn_indices_rows(x_rows, B, N, k):
+    """Point-major rows [B*N, C] -> idx int32 [B, N, k], the same neighbour lists as knn_indices on the [B, C, N]
+    view (bit for bit).  Runs the tensor-core filter + exact refine kernel when the shape allows, else transposes and
+    calls the CUDA-core kernel."""
+    global LAST_KNN_WORKSPACE
+    x = _c(x_rows.detach())
+    C = x.shape[1]
+    ws_bytes = L().knn_rows_workspace(B, C, N, k) if KNN_TC else 0
+    if ws_bytes == 0:
+        return knn_indices(RowsToBcn.apply(x, B, C, N), k)
+    xs = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    L().sqnorm_pm(x.data_ptr(), B, C, N, -1, xs.data_ptr(), _stream())
+    idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
+    ws = torch.empty(ws_bytes // 4, device=x.device, dtype=torch.int32)
+    LAST_KNN_WORKSPACE = ws
+    L().knn_rows(x.data_ptr(), xs.data_ptr(), B, C, N, k, idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+    return idx
+
+
 def idx_to_int64(idx32):
     out = torch.empty(idx32.shape, device=idx32.device, dtype=torch.int64)
     L().idx32_to_idx64(idx32.data_ptr(), out.data_ptr(), idx32.numel(), _stream())

@@ -118,3 +118,60 @@ def test_c_abi_rejects_bad_k():
         ops.knn_indices(x, 40)
     with pytest.raises(m.SpganError):
         ops.knn_indices(torch.zeros((1, 3, 4), device="cuda"), 4)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core filter + exact refine on point-major rows (csrc/knn_tc.cu): bit-identical to the CUDA-core kernel
+def _rows_of(x_bcn):
+    B, C, N = x_bcn.shape
+    return np.ascontiguousarray(x_bcn.transpose(0, 2, 1)).reshape(B * N, C)
+
+
+def _tc_vs_exact(x_bcn, k, expect_no_fallback):
+    import spgan_b200 as pkg
+    ops = pkg.ops
+    B, C, N = x_bcn.shape
+    assert ops.L().knn_rows_workspace(B, C, N, k) > 0, "shape should be inside the tensor-core kernel's envelope"
+    got = ops.knn_indices_rows(torch.from_numpy(_rows_of(x_bcn)).cuda(), B, N, k).cpu().numpy()
+    fallbacks = int(ops.LAST_KNN_WORKSPACE[1])
+    want = ops.knn_indices(torch.from_numpy(x_bcn).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, want), "%d of %d entries differ" % ((got != want).sum(), got.size)
+    if expect_no_fallback:
+        # the threshold is an upper bound (group minima): a rare query collects more than 16 candidates in one half
+        # and is ranked by the exact scan instead -- same result, slower
+        assert fallbacks <= max(2, B * N // 20000), fallbacks
+    return fallbacks
+
+
+@pytest.mark.parametrize("B,C,N,k", [(4, 64, 2048, 10), (2, 128, 1024, 15), (3, 16, 256, 5), (1, 256, 128, 8),
+                                     (2, 100, 384, 10), (64, 64, 2048, 10)])
+def test_tc_filter_refine_matches_exact_kernel(B, C, N, k):
+    rng = np.random.default_rng(B * 7 + C + N)
+    x = rng.standard_normal((B, C, N)).astype(np.float32)
+    _tc_vs_exact(x, k, expect_no_fallback=True)
+    if B * N * N * C <= 3e8:                                     # and against the C oracle where it is affordable
+        import spgan_b200 as pkg
+        got = pkg.ops.knn_indices_rows(torch.from_numpy(_rows_of(x)).cuda(), B, N, k).cpu().numpy()
+        assert np.array_equal(got, knn_ref.knn(x, k))
+
+
+def test_tc_filter_refine_on_clustered_dense_and_degenerate_clouds():
+    """The margin only decides how many candidates reach the exact stage, never the result: clustered features with a
+    large common offset (cancellation, exact ties), a coarse grid (many equal distances), duplicated points (candidate
+    lists overflow: the exact scan takes over), non-finite rows."""
+    rng = np.random.default_rng(11)
+    clustered = (1.0 + 0.05 * rng.standard_normal((2, 64, 1024))).astype(np.float32)
+    _tc_vs_exact(clustered, 10, expect_no_fallback=False)
+    grid = (rng.integers(0, 4, (2, 16, 512)) * 0.5).astype(np.float32)
+    _tc_vs_exact(grid, 10, expect_no_fallback=False)
+    dup = rng.standard_normal((1, 64, 1024)).astype(np.float32)
+    dup[0, :, 512:] = dup[0, :, :512]                            # every point twice
+    dup[0, :, :40] = dup[0, :, :1]                               # and one point 40 times: lists overflow
+    fb = _tc_vs_exact(dup, 10, expect_no_fallback=False)
+    assert fb > 0
+    bad = rng.standard_normal((2, 64, 256)).astype(np.float32)
+    bad[0, :, 5] = np.nan
+    bad[1, 7, :] = np.inf
+    _tc_vs_exact(bad, 10, expect_no_fallback=False)
+    big = (1e3 * rng.standard_normal((1, 64, 512))).astype(np.float32)     # large magnitudes (fp16 range of the split)
+    _tc_vs_exact(big, 10, expect_no_fallback=False)
