@@ -474,21 +474,28 @@ def run_gpu(args, real_stdout):
                 roofline = dict(roofline_all, traffic=None, peak_source=peak_src)
         else:
             roofline_all = None
-        kn = [(ia, s_.elapsed_time(e_)) for name, ia, s_, e_ in prof if name == "spgan_knn_group"]
+        kn = [(name, ia, s_.elapsed_time(e_)) for name, ia, s_, e_ in prof if name in ("spgan_knn_group", "spgan_knn_rows")]
         roofline_knn = None
         if kn:
-            ia, t_ms = max(kn, key=lambda kv: kv[0][1])              # (B, C, N, k): the C = 64 launch
+            name, ia, t_ms = max(kn, key=lambda kv: kv[1][1])        # (B, C, N, k): the C = 64 launch (EdgeConv2's graph)
             Bk, Ck, Nk, kk = ia[0], ia[1], ia[2], ia[3]
             fl = 2.0 * Bk * Nk * Nk * Ck
             byts = 4.0 * (Bk * Ck * Nk + Bk * Nk * kk)
             ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-            roofline_knn = {"kernel": "knn_group_fast_kernel B=%d C=%d N=%d k=%d (bit-exact fp32 recipe: CUDA cores only)" % (Bk, Ck, Nk, kk),
-                            "bound": "fp32 FFMA + selection", "ms": t_ms, "achieved": fl / (t_ms / 1e3) / 1e12,
-                            "peak": ffma_peak, "unit": "TFLOP/s", "frac": fl / (t_ms / 1e3) / 1e12 / ffma_peak,
-                            "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+            tc = name == "spgan_knn_rows"
+            roofline_knn = {"kernel": ("knn_tc_filter + knn_tc_refine (tcgen05 filter, exact fp32 refine: bit-exact lists)" if tc else
+                                       "knn_group_fast_kernel (bit-exact fp32 recipe: CUDA cores only)") +
+                                      " B=%d C=%d N=%d k=%d" % (Bk, Ck, Nk, kk),
+                            "bound": "tensor (filter: 2 passes x 3 MMAs per product) + L2 gather (refine)" if tc else "fp32 FFMA + selection",
+                            "ms": t_ms, "achieved": fl / (t_ms / 1e3) / 1e12, "peak": ffma_peak, "unit": "TFLOP/s (algorithmic 2 B N^2 C)",
+                            "frac": fl / (t_ms / 1e3) / 1e12 / ffma_peak,
+                            "peak_source": "nominal fp32 FFMA: 148 SM x 128 lanes x 2 x 1.965 GHz (what an all-pairs fp32 kernel is bound by)",
                             "hbm_algorithmic_bytes": byts, "hbm_gbs": byts / (t_ms / 1e3) / 1e9,
                             "hbm_frac_of_measured": byts / (t_ms / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
-                            "traffic": ncu.get("knn_group_fast_kernel", {}).get("dram_traffic_bytes")}
+                            "traffic": ncu.get("knn_tc_filter_kernel" if tc else "knn_group_fast_kernel", {}).get("dram_traffic_bytes")}
+            if tc:
+                roofline_knn["tensor_tflops_executed"] = 6.0 * fl / (t_ms / 1e3) / 1e12
+                roofline_knn["frac_of_bf16_peak_executed"] = 6.0 * fl / (t_ms / 1e3) / 1e12 / peak_tf()
 
     # ---- sub-metrics of BASELINE's metric string: "kNN+EdgeConv ms/batch" and configs[1] (generator forward only)
     sub = None
@@ -508,15 +515,16 @@ def run_gpu(args, real_stdout):
             x1_bcn = pkg.ops.RowsToBcn.apply(x1, B, x1.shape[1], N)
             pc_rows = x.reshape(B * N, 3)
             pc_bcn = pkg.ops.RowsToBcn.apply(pc_rows, B, 3, N)
-            knn2 = ev_ms(lambda: pkg.ops.knn_indices(x1_bcn, G.nk))
+            knn2 = ev_ms(lambda: pkg.ops.knn_indices_rows(x1, B, N, G.nk))          # what the generator calls
+            knn2_cuda_core = ev_ms(lambda: pkg.ops.knn_indices(x1_bcn, G.nk))
             knn1 = ev_ms(lambda: pkg.ops.knn_indices(pc_bcn, G.nk))
-            idx2 = pkg.ops.knn_indices(x1_bcn, G.nk)
+            idx2 = pkg.ops.knn_indices_rows(x1, B, N, G.nk)
             idx1 = pkg.ops.knn_indices(pc_bcn, G.nk)
             ec2 = ev_ms(lambda: G.EdgeConv2.forward_rows(x1, idx2, B, N))
             ec1 = ev_ms(lambda: G.EdgeConv1.forward_rows(pc_rows, idx1, B, N))
         sub = {"generator_forward_ms_per_batch": g_fwd, "generator_forward_clouds_per_s": B / (g_fwd / 1e3),
                "knn_edgeconv_ms_per_batch": knn1 + knn2 + ec1 + ec2,
-               "knn_C3_ms": knn1, "knn_C64_ms": knn2, "edgeblock1_fwd_ms": ec1, "edgeblock2_fwd_ms": ec2,
+               "knn_C3_ms": knn1, "knn_C64_ms": knn2, "knn_C64_cuda_core_kernel_ms": knn2_cuda_core, "edgeblock1_fwd_ms": ec1, "edgeblock2_fwd_ms": ec2,
                "note": "forward, train-mode BN, B=%d N=%d k=%d; the C=3 graph of the static sphere is cached inside "
                        "training steps (model.py:231) but counted here" % (B, N, G.nk)}
 

@@ -415,7 +415,25 @@ __device__ __forceinline__ bool key_less(float d0, int j0, float d1, int j1) { r
 __device__ __forceinline__ float recipe_dist(const float* __restrict__ xi, const float* __restrict__ xj, int C, float xs_i,
                                              float xs_j) {
     float acc = 0.f;
-    for (int c = 0; c < C; c += 4) {
+    int c = 0;
+    // 32 channels per step: all 16 loads of the step are issued before the (sequential, channel-order) FMA chain
+    // consumes them -- the candidate rows are scattered over L2, a dependent load per FMA group costs a round trip
+    for (; c + 32 <= C; c += 32) {
+        float4 a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a[u] = __ldg(reinterpret_cast<const float4*>(xi + c) + u);
+            b[u] = __ldg(reinterpret_cast<const float4*>(xj + c) + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            acc = __fmaf_rn(a[u].x, b[u].x, acc);
+            acc = __fmaf_rn(a[u].y, b[u].y, acc);
+            acc = __fmaf_rn(a[u].z, b[u].z, acc);
+            acc = __fmaf_rn(a[u].w, b[u].w, acc);
+        }
+    }
+    for (; c < C; c += 4) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(xi + c)), b = __ldg(reinterpret_cast<const float4*>(xj + c));
         acc = __fmaf_rn(a.x, b.x, acc);
         acc = __fmaf_rn(a.y, b.y, acc);
@@ -426,7 +444,7 @@ __device__ __forceinline__ float recipe_dist(const float* __restrict__ xi, const
 }
 
 // one warp per query
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 knn_tc_refine_kernel(const float* __restrict__ rows, const float* __restrict__ xs, const int32_t* __restrict__ cand,
                      const int32_t* __restrict__ cnt, int B, int N, int C, int k, int32_t* __restrict__ idx,
                      int* __restrict__ fallbacks) {
@@ -569,6 +587,6 @@ extern "C" int spgan_knn_rows(const float* rows, const float* xs, int B, int C, 
     }
     rc = spgan_launch_status();
     if (rc != SPGAN_OK) return rc;
-    knn_tc_refine_kernel<<<kNumSMs * 8, 256, 0, st>>>(rows, xs, cand, cnt, B, N, C, k, idx, status + 1);
+    knn_tc_refine_kernel<<<kNumSMs * 16, 256, 0, st>>>(rows, xs, cand, cnt, B, N, C, k, idx, status + 1);
     return spgan_launch_status();
 }
