@@ -15,7 +15,7 @@ out = torch.empty(M, N, device="cuda")
 sc, sh = torch.rand(K, device="cuda") + 0.5, torch.randn(K, device="cuda")
 for _ in range(4):
     if pro:
-        pkg.ops.gemm_fused_raw(A, B, None, tb=True, out=out, a_scale=sc, a_shift=sh, a_slope=0.01, want_stats=True)
+        pkg.ops.gemm_fused_raw(A, B, None, tb=True, out=out, a_scale=sc, a_shift=sh, a_slope=0.01, want_stats=N <= 256)
     else:
         pkg.ops.gemm_fused_raw(A, B, None, tb=True, out=out)
 torch.cuda.synchronize()

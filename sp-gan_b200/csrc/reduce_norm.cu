@@ -1072,16 +1072,27 @@ extern "C" int spgan_colstats_bn(const float* x, int64_t R, int C, float eps, fl
 }
 
 // Column partial sums of a GEMM epilogue (spgan_gemm_fused) -> batch statistics, the consumer's prologue tables and
-// the running-statistics update, one thread per column, partials added in double in row order (deterministic).
-__global__ void bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int rows, int C, double inv_n,
-                                   float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ var,
-                                   float* __restrict__ scale, float* __restrict__ shift, float momentum, float unbias,
-                                   float* rm, float* rv, int64_t* count) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// the running-statistics update; partials added in double along a fixed tree (deterministic).
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ ps, const float* __restrict__ pq, int rows, int C, double inv_n,
+                   float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ var,
+                   float* __restrict__ scale, float* __restrict__ shift, float momentum, float unbias,
+                   float* rm, float* rv, int64_t* count) {
+    // block = 32 columns x 32 row lanes; every lane adds its rows in order, the 32 lane sums are combined in order:
+    // a fixed summation tree (deterministic), in double
+    __shared__ double red[2][32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     double s1 = 0.0, s2 = 0.0;
-    for (int r = 0; r < rows; ++r) { s1 += (double)ps[(int64_t)r * C + c]; s2 += (double)pq[(int64_t)r * C + c]; }
+    if (c < C)
+        for (int r = ty; r < rows; r += 32) { s1 += (double)__ldg(ps + (int64_t)r * C + c); s2 += (double)__ldg(pq + (int64_t)r * C + c); }
+    red[0][ty][tx] = s1;
+    red[1][ty][tx] = s2;
+    __syncthreads();
+    if (ty != 0 || c >= C) return;
+    s1 = 0.0; s2 = 0.0;
+    for (int t = 0; t < 32; ++t) { s1 += red[0][t][tx]; s2 += red[1][t][tx]; }
     const double m = s1 * inv_n;
     double v = s2 * inv_n - m * m;
     if (v < 0.0) v = 0.0;
@@ -1106,7 +1117,7 @@ extern "C" int spgan_bn_finalize(const float* col_sum, const float* col_sqsum, i
     SPGAN_CHECK_ARG(col_sum && col_sqsum && mean && rstd && var && rows >= 1 && C >= 1 && R >= 1);
     SPGAN_CHECK_ARG((scale == nullptr) == (shift == nullptr) && (rm == nullptr) == (rv == nullptr));
     const float unbias = R > 1 ? (float)((double)R / (double)(R - 1)) : 1.f;
-    bn_finalize_kernel<<<(C + 63) / 64, 64, 0, as_stream(s)>>>(col_sum, col_sqsum, rows, C, 1.0 / (double)R, eps, gamma, beta,
+    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, as_stream(s)>>>(col_sum, col_sqsum, rows, C, 1.0 / (double)R, eps, gamma, beta,
                                                                mean, rstd, var, scale, shift, momentum, unbias, rm, rv, count);
     return spgan_launch_status();
 }
