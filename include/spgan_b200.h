@@ -65,7 +65,8 @@ int spgan_sqnorm_pm(const float *x_rows, int B, int C, int N, int main_cols, flo
  * proven error margin of its (k+1)-th smallest approximate distance; the reference's exact fp32 recipe then ranks only
  * those (a handful per query) by (dist, index).  Bit-identical to spgan_knn_group on the same points; queries whose
  * candidate list overflows or comes up short (duplicate-heavy or non-finite clouds) are ranked by an exact scan.
- * xs from spgan_sqnorm_pm.  N % 128 == 0, 16 <= C <= 256, C % 4 == 0, k <= 15.
+ * xs from spgan_sqnorm_pm.  N % 128 == 0, N <= 4096, 4 <= C <= 256, C % 4 == 0, k <= 15 (a channel count that is not
+ * a multiple of 4 may be zero-padded by the caller: zero channels change neither the FMA chain nor the norms).
  * spgan_knn_rows_workspace returns the workspace bytes (256-byte aligned buffer) or 0 when the shape is outside the
  * envelope (the caller then uses spgan_knn_group).  workspace[1] (int32) counts the queries ranked by the exact scan. */
 size_t spgan_knn_rows_workspace(int B, int C, int N, int k);
@@ -167,6 +168,9 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  *             both need a workspace of spgan_gemm_workspace(engine, N, K) bytes (256-byte aligned).
  *             Anything else runs on engine 0, which uses the workspace (if given) for deterministic
  *             split-K partial tiles when M <= 128 and 256 <= K < 2048 (the small-batch MLPs).
+ * Weight reuse: the tensor engines first split op(B) into the workspace.  A caller that multiplies by the same weight
+ * again (same B, N, K, transB, same engine route) may pass the SAME workspace with bit 1 of transB set (transB | 2):
+ * the split is then skipped (also honoured by spgan_gemm_fused).
  * The first int of the workspace is a status word: non-zero after completion means the kernel
  * aborted on an internal pipeline timeout (never expected; checked by the tests). */
 size_t spgan_gemm_workspace(int engine, int N, int K);

@@ -329,17 +329,19 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
                           const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate,
                           int engine, void* workspace, size_t workspace_bytes, spgan_stream_t stream) {
     SPGAN_CHECK_ARG(A && B && C && M >= 0 && N >= 1 && K >= 1);
+    const int presplit = transB & 2;     // tensor engines only: the workspace holds the split weight of an earlier call
+    transB &= 1;
     SPGAN_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N);
     if (M == 0) return SPGAN_OK;
     // engine 3, K <= 256: the TMEM-resident-A kernel (gemm_ts.cu); SPGAN_TS=0 routes these to gemm_tc.cu instead
     if (engine == 3 && !transA && workspace != nullptr && ts_enabled() && spgan_gemm_ts_supported(M, N, K, A, lda) &&
         workspace_bytes >= spgan_gemm_ts_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
-        return spgan_gemm_ts(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, nullptr, 1.f, nullptr,
+        return spgan_gemm_ts(transB | presplit, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, nullptr, 1.f, nullptr,
                              nullptr, workspace, as_stream(stream));
     // tcgen05 engines: 1 = TF32x3, 2 = BF16x3, 3 = FP16Sx3 (gemm_tc.cu) for the forward / dgrad products
     if (engine >= 1 && engine <= 3 && workspace != nullptr && spgan_gemm_tc_supported(transA, M, N, K) &&
         workspace_bytes >= spgan_gemm_tc_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
-        return spgan_gemm_tc(engine - 1, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
+        return spgan_gemm_tc(engine - 1, transB | presplit, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, workspace,
                              as_stream(stream));
     // weight gradients: C[M,N] = A^T B with A [K,M], B [K,N], K = #points.  Engine 3: the TMA / TMEM kernel with
     // deterministic split-K partials (gemm_wg.cu) when the caller's workspace holds them; SPGAN_WG=0 disables it
@@ -376,7 +378,7 @@ extern "C" int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float
                                 const float* a_scale, const float* a_shift, float a_slope, float* col_sum,
                                 float* col_sqsum, void* workspace, size_t workspace_bytes, spgan_stream_t stream) {
     SPGAN_CHECK_ARG(A && B && C && workspace && M >= 1 && N >= 1 && K >= 1);
-    SPGAN_CHECK_ARG(lda >= K && ldb >= (transB ? K : N) && ldc >= N);
+    SPGAN_CHECK_ARG(lda >= K && ldb >= ((transB & 1) ? K : N) && ldc >= N);
     SPGAN_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr) && (col_sum == nullptr) == (col_sqsum == nullptr));
     if (col_sum != nullptr && N > 256) return SPGAN_E_UNSUPPORTED;     // column statistics: up to 4 column tiles
     if (!spgan_gemm_ts_supported(M, N, K, A, lda) || workspace_bytes < spgan_gemm_ts_workspace(N, K) ||

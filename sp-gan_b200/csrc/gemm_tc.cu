@@ -586,9 +586,12 @@ int run_tc(int transB, int64_t M, int N, int K, const float* A, int64_t lda, con
     int* status = reinterpret_cast<int*>(ws);
     unsigned char* hi = ws + 256;
     unsigned char* lo = hi + align_up(align_up((size_t)N, 256) * Kp * ESZ, 256);
-    presplit_b_kernel<MODE><<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, Npad, Kp, hi, lo, status);
-    int rc = spgan_launch_status();
-    if (rc != SPGAN_OK) return rc;
+    int rc = SPGAN_OK;
+    if ((transB & 2) == 0) {             // bit 1 of transB: the workspace already holds this weight's split operand
+        presplit_b_kernel<MODE><<<ew_grid((int64_t)Npad * Kp, 256), 256, 0, st>>>(B, ldb, transB & 1, N, K, Npad, Kp, hi, lo, status);
+        rc = spgan_launch_status();
+        if (rc != SPGAN_OK) return rc;
+    }
     if (BN == 64) return launch_tc<64, MODE>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
     if (BN == 128) return launch_tc<128, MODE>(M, N, K, A, lda, hi, lo, Kp, Npad, C, ldc, bias, accumulate, status, st);
     if constexpr (MODE == MODE_BF16)

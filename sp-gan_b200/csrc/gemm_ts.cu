@@ -515,9 +515,12 @@ int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t l
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     int* status = reinterpret_cast<int*>(ws);
     uint16_t* wsplit = reinterpret_cast<uint16_t*>(ws + 256);
-    presplit_w_kernel<<<ew_grid((int64_t)n_tiles * BN * Kp, 256), 256, 0, st>>>(B, ldb, transB, N, K, n_tiles, Kp, wsplit, status);
-    int rc = spgan_launch_status();
-    if (rc != SPGAN_OK) return rc;
+    int rc = SPGAN_OK;
+    if ((transB & 2) == 0) {             // bit 1 of transB: the workspace already holds this weight's split tiles
+        presplit_w_kernel<<<ew_grid((int64_t)n_tiles * BN * Kp, 256), 256, 0, st>>>(B, ldb, transB & 1, N, K, n_tiles, Kp, wsplit, status);
+        rc = spgan_launch_status();
+        if (rc != SPGAN_OK) return rc;
+    }
 
     CUtensorMap tmA, tmB;
     {

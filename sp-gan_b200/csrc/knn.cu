@@ -532,10 +532,6 @@ extern "C" int spgan_sqnorm(const float* x, int B, int C, int N, int main_cols, 
     return spgan_launch_status();
 }
 
-// knn_ws.cu: opt-in warp-specialised variant (SPGAN_KNN_WS=1), same neighbour lists
-bool spgan_knn_ws_enabled();
-int spgan_knn_ws_launch(const float* x, const float* xs, int B, int C, int N, int k, int32_t* idx, cudaStream_t st);
-
 extern "C" int spgan_knn_group(const float* x, const float* xs, int B, int C, int N, int k, int32_t* idx,
                                float* ee, spgan_stream_t stream) {
     SPGAN_CHECK_ARG(x && xs && idx && B >= 0 && C >= 1 && N >= 1 && k >= 1);
@@ -550,10 +546,6 @@ extern "C" int spgan_knn_group(const float* x, const float* xs, int B, int C, in
     const int64_t grid = (int64_t)B * q_tiles;
     if (grid > 0x7fffffffLL) return SPGAN_E_UNSUPPORTED;
     if (N % 4 == 0 && N >= CT && C <= QMAXC && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        if (ee == nullptr && spgan_knn_ws_enabled()) {
-            const int rc = spgan_knn_ws_launch(x, xs, B, C, N, k, idx, as_stream(stream));
-            if (rc != SPGAN_E_UNSUPPORTED) return rc;
-        }
         static_assert(sizeof(KnnFastSmem) <= 104 * 1024, "two CTAs per SM");
         e = cudaFuncSetAttribute(knn_group_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(KnnFastSmem));

@@ -523,7 +523,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 }  // namespace
 
 extern "C" size_t spgan_knn_rows_workspace(int B, int C, int N, int k) {
-    if (B < 1 || N < BM || N % BM != 0 || C < 16 || C > MAX_KB * BK || C % 4 != 0 || k < 1 || k + 1 > KL || k + 1 > N ||
+    if (B < 1 || N < BM || N % BM != 0 || C < 4 || C > MAX_KB * BK || C % 4 != 0 || k < 1 || k + 1 > KL || k + 1 > N ||
         N > MAX_N || (int64_t)B * N >= (1LL << 31) || encode_tiled_fn() == nullptr)
         return 0;
     const size_t R = (size_t)B * N, Kp = align_up((size_t)C, BK);

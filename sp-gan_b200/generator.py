@@ -188,7 +188,7 @@ class Generator(nn.Module):
         cached on (storage, version, shape) of `x` (with `x` itself kept alive) and recomputed whenever `x` changes."""
         if self.debug_idx is not None and self.debug_idx[0] is not None:
             return self.debug_idx[0]
-        knn = lambda: ops.knn_indices(ops.RowsToBcn.apply(pc_rows.detach(), B, pc_rows.shape[1], N), self.nk)
+        knn = lambda: ops.knn_indices_rows(pc_rows, B, N, self.nk)
         if not self.cache_sphere_graph or self.use_head:
             return knn()
         # The entry keeps a strong reference to `x`: while it lives, its storage cannot be freed and handed to a

@@ -10,6 +10,8 @@ Layout: activations are point-major rows [R, C] (R = B*N points or B*N*k edges).
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -140,7 +142,48 @@ LAST_TC_WORKSPACE = None      # most recent tcgen05 workspace (its first int is 
 _TN_STATUS = {}               # per-device zeroed status block of the weight-gradient kernel
 
 
-def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, engine=None):
+# Split-weight cache: the tensor engines split every fp32 weight into fp16 hi / lo tiles before the product.  Within
+# one optimiser phase the same weight is multiplied many times (the critic runs five times per step), so the split
+# workspace of a PARAMETER is kept and re-used (transB | 2 in the C ABI) until the weights change: every in-place
+# update bumps the tensor version, FlatAdam (raw-pointer update) calls weights_changed().
+_WCACHE = {}
+WEIGHT_EPOCH = 0
+WEIGHT_CACHE = _os.environ.get("SPGAN_WEIGHT_CACHE", "1") != "0"
+
+
+def weights_changed():
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+    _WCACHE.clear()
+
+
+def _param_of(t):
+    """The nn.Parameter `t` is (a view of), or None."""
+    if isinstance(t, torch.nn.Parameter):
+        return t
+    base = t._base
+    return base if base is not None and isinstance(base, torch.nn.Parameter) else None
+
+
+def _cached_ws(kind, Bm, tb, extra, ws_bytes, device):
+    """-> (workspace, flag): flag 2 = the workspace already holds the split of this weight.  Entries are tied to the
+    Parameter OBJECT (weak reference), not to its address: a freed parameter's address, shape and version can all
+    recur in another module."""
+    param = _param_of(Bm)
+    if param is None:
+        return torch.empty(ws_bytes // 4 + 64, device=device, dtype=torch.float32), 0
+    key = (kind, id(param), Bm.data_ptr(), Bm._version, tuple(Bm.shape), tuple(Bm.stride()), bool(tb), extra, WEIGHT_EPOCH)
+    ent = _WCACHE.get(key)
+    if ent is not None and ent[1]() is param:
+        return ent[0], 2
+    ws = torch.empty(ws_bytes // 4 + 64, device=device, dtype=torch.float32)
+    if len(_WCACHE) > 512:
+        _WCACHE.clear()
+    _WCACHE[key] = (ws, weakref.ref(param))
+    return ws, 0
+
+
+def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, engine=None, wcache=False):
     global LAST_TC_WORKSPACE
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
@@ -155,7 +198,7 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
     if bias is not None:
         bias = _c(bias)
     engine = GEMM_ENGINE if engine is None else engine
-    ws, ws_bytes = None, 0
+    ws, ws_bytes, wflag = None, 0, 0
     tc = engine in (1, 2, 3) and ((not ta and M >= 128 and N >= 16 and K >= 16) or
                                (ta and not tb and bias is None and K >= 4096 and M >= 16 and N >= 16))
     if tc and ta:
@@ -173,17 +216,22 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
         LAST_TC_WORKSPACE = ws
     elif tc or (M <= 128 and 256 <= K < 2048):       # pre-split weight operand / small-batch split-K partial tiles
         ws_bytes = L().gemm_workspace(engine, N, K)
-        ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
+        if tc and wcache and WEIGHT_CACHE:
+            # the route (gemm_ts vs gemm_tc) is part of the key: it fixes the layout of the split
+            route = engine == 3 and L().gemm_fused_workspace(M, N, K, A.data_ptr(), lda) != 0
+            ws, wflag = _cached_ws("gemm", B, tb, (engine, route), ws_bytes, A.device)
+        else:
+            ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
         if tc:
             LAST_TC_WORKSPACE = ws
-    L().gemm(int(ta), int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
+    L().gemm(int(ta), int(tb) | wflag, M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
              bias.data_ptr() if bias is not None else None, int(accumulate), engine,
              ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
     return out
 
 
 def gemm_fused_raw(A, B, bias=None, tb=True, out=None, accumulate=False, a_scale=None, a_shift=None, a_slope=1.0,
-                   want_stats=False):
+                   want_stats=False, wcache=False):
     """spgan_gemm_fused: C = lrelu(A * a_scale + a_shift) @ op(B) + bias, optionally with the per-column partial sums
     of C and C^2 (-> (C, col_sum, col_sqsum)).  Returns None when the shape is outside the fused kernel's envelope."""
     global LAST_TC_WORKSPACE
@@ -196,14 +244,18 @@ def gemm_fused_raw(A, B, bias=None, tb=True, out=None, accumulate=False, a_scale
         return None
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
-    ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
+    wflag = 0
+    if wcache and WEIGHT_CACHE:
+        ws, wflag = _cached_ws("fused", B, tb, None, ws_bytes, A.device)
+    else:
+        ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)
     LAST_TC_WORKSPACE = ws
     cs = cq = None
     if want_stats:
         rows = L().gemm_fused_stats_rows(M)
         cs = torch.empty((rows, N), device=A.device, dtype=torch.float32)
         cq = torch.empty((rows, N), device=A.device, dtype=torch.float32)
-    L().gemm_fused(int(tb), M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
+    L().gemm_fused(int(tb) | wflag, M, N, K, A.data_ptr(), lda, B.data_ptr(), ldb, out.data_ptr(), _ld(out),
                    bias.data_ptr() if bias is not None else None, int(accumulate),
                    a_scale.data_ptr() if a_scale is not None else None,
                    a_shift.data_ptr() if a_shift is not None else None, float(a_slope),
@@ -238,7 +290,7 @@ class Gemm(Function):
         ctx.save_for_backward(A, B)
         ctx.has_bias = bias is not None
         ctx.zero_bias_grad = zero_bias_grad
-        return gemm_raw(A, _wmat(B, cols), bias, ta, tb, engine=engine)
+        return gemm_raw(A, _wmat(B, cols), bias, ta, tb, engine=engine, wcache=True)
 
     @staticmethod
     def backward(ctx, g):
@@ -846,7 +898,8 @@ class BnActLinearTrain(Function):
         R = x_pre.shape[0]
         Wm = _wmat(W, None)
         want = next_bn is not None
-        res = gemm_fused_raw(x_pre, Wm, bias, tb=True, a_scale=scale, a_shift=shift, a_slope=slope, want_stats=want)
+        res = gemm_fused_raw(x_pre, Wm, bias, tb=True, a_scale=scale, a_shift=shift, a_slope=slope, want_stats=want,
+                             wcache=True)
         if res is None:
             raise RuntimeError("BnActLinearTrain: shape outside spgan_gemm_fused's envelope (caller must check fused_linear_ok)")
         ctx.slope, ctx.zero_bias_grad, ctx.has_bias = slope, zero_bias_grad, bias is not None
@@ -890,7 +943,7 @@ class BnActLinearTrain(Function):
         if ctx.has_bias and ctx.needs_input_grad[8] and params_too and not ctx.zero_bias_grad:
             db = ColSum.apply(gz, R).view(-1)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
-            ga = gemm_raw(gz, Wm, None, False, False)         # d(activated input)
+            ga = gemm_raw(gz, Wm, None, False, False, wcache=True)         # d(activated input)
             acc = (gamma, beta) if (ctx.needs_input_grad[5] and ctx.needs_input_grad[6] and params_too
                                     and _direct_ok(gamma, beta)) else None
             dx, sg, sgx = _norm_bwd(ga, x_pre, ctx.slope, R, mean, rstd, gamma, beta, acc)
@@ -1397,6 +1450,14 @@ def knn_indices_rows(x_rows, B, N, k):
     global LAST_KNN_WORKSPACE
     x = _c(x_rows.detach())
     C = x.shape[1]
+    if KNN_TC and C % 4 != 0 and L().knn_rows_workspace(B, (C + 3) // 4 * 4, N, k) != 0:
+        # zero-pad the channels to a multiple of 4 (TMA row pitch): fma(0, 0, acc) = acc and acc + 0*0 = acc exactly,
+        # so the recipe's distances -- and the lists -- are unchanged (the xyz sphere of EdgeConv1: C = 3 -> 4)
+        pad = (C + 3) // 4 * 4 - C
+        xp = torch.empty((x.shape[0], C + pad), device=x.device, dtype=torch.float32)
+        zeros = full((1, pad), 0.0, x.device)
+        L().concat_cols(x.data_ptr(), C, C, zeros.data_ptr(), 0, 0, x.shape[0], pad, x.shape[0], xp.data_ptr(), _stream())
+        x, C = xp, C + pad
     ws_bytes = L().knn_rows_workspace(B, C, N, k) if KNN_TC else 0
     if ws_bytes == 0:
         return knn_indices(RowsToBcn.apply(x, B, C, N), k)

@@ -65,6 +65,7 @@ class FlatAdam:
 
     def step(self):
         scale = self.buf.allreduce_grads()
+        ops.weights_changed()              # the update below goes through raw pointers: drop the split-weight cache
         ops.L().adam_step_dev(self.buf.flat_p.data_ptr(), self.buf.flat_g.data_ptr(), self.m.data_ptr(),
                               self.v.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
                               self.state.data_ptr(), scale, ops._stream())
@@ -80,6 +81,7 @@ class WGANGPTrainer:
         self.opt_d = FlatAdam(D, lr_d, betas)
         self.opt_g.buf.broadcast_params()
         self.opt_d.buf.broadcast_params()
+        ops.weights_changed()              # parameters were re-pointed / broadcast: no split-weight cache entry survives
         self._graph, self._graph_out, self._static, self.graph_launches = None, None, None, 0
 
     def d_phase(self, x, z, real, alpha=None):
@@ -135,6 +137,7 @@ class WGANGPTrainer:
                 self.step(st["x"], st["z_d"], st["z_g"], st["real"], st["alpha"])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        ops.weights_changed()              # nothing split outside the graph may be referenced from inside it
         l0 = ops.L().launches
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -164,3 +164,33 @@ def test_wgrad_engine3_matches_fp64_and_is_deterministic(Mo, No, K):
     emax, el2 = rel_err((wide[:, 4:4 + No] - 1).cpu().numpy(), ref.numpy())
     assert emax < 8e-5 and el2 < 1.6e-5, (emax, el2)
     assert float(wide[:, :4].min()) == 1.0 and float(wide[:, 4 + No:].max()) == 1.0
+
+
+def test_split_weight_cache_follows_the_parameter():
+    """The split (fp16 hi / lo) of a Parameter is kept across products until the parameter changes: in-place updates
+    bump its version, raw-pointer updates announce themselves through ops.weights_changed()."""
+    import torch.nn as nn
+    ops = _ops()
+    ops.weights_changed()
+    W = nn.Parameter(_rnd(96, 128, seed=1).cuda())
+    b = nn.Parameter(_rnd(96, seed=2).cuda())
+    x = _rnd(4096, 128, seed=3).cuda()
+    ref = lambda: (x.double() @ W.detach().double().t() + b.detach().double()).cpu().numpy()
+    y1 = ops.linear(x, W, b)
+    n_entries = len(ops._WCACHE)
+    assert n_entries >= 1
+    y2 = ops.linear(x, W, b)                               # served from the cache
+    assert len(ops._WCACHE) == n_entries and torch.equal(y1, y2)
+    assert rel_err(y2.detach().cpu().numpy(), ref())[1] < 2e-6
+    with torch.no_grad():
+        W.mul_(0.5)                                        # version bump: the old split must not be used
+    y3 = ops.linear(x, W, b)
+    assert rel_err(y3.detach().cpu().numpy(), ref())[1] < 2e-6
+    ops.L().axpby(2.0, W.data_ptr(), 0.0, None, W.data_ptr(), W.numel(), ops._stream())     # raw-pointer update
+    ops.weights_changed()
+    y4 = ops.linear(x, W, b)
+    assert rel_err(y4.detach().cpu().numpy(), ref())[1] < 2e-6
+    # a non-parameter operand is never cached
+    before = len(ops._WCACHE)
+    ops.gemm_raw(x, W.detach().clone(), None, False, True, wcache=True)
+    assert len(ops._WCACHE) == before

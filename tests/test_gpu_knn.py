@@ -131,7 +131,7 @@ def _tc_vs_exact(x_bcn, k, expect_no_fallback):
     import spgan_b200 as pkg
     ops = pkg.ops
     B, C, N = x_bcn.shape
-    assert ops.L().knn_rows_workspace(B, C, N, k) > 0, "shape should be inside the tensor-core kernel's envelope"
+    assert ops.L().knn_rows_workspace(B, (C + 3) // 4 * 4, N, k) > 0, "shape should be inside the tensor-core kernel's envelope"
     got = ops.knn_indices_rows(torch.from_numpy(_rows_of(x_bcn)).cuda(), B, N, k).cpu().numpy()
     fallbacks = int(ops.LAST_KNN_WORKSPACE[1])
     want = ops.knn_indices(torch.from_numpy(x_bcn).cuda(), k).cpu().numpy()
@@ -144,7 +144,7 @@ def _tc_vs_exact(x_bcn, k, expect_no_fallback):
 
 
 @pytest.mark.parametrize("B,C,N,k", [(4, 64, 2048, 10), (2, 128, 1024, 15), (3, 16, 256, 5), (1, 256, 128, 8),
-                                     (2, 100, 384, 10), (64, 64, 2048, 10)])
+                                     (2, 100, 384, 10), (64, 64, 2048, 10), (3, 3, 2048, 10), (2, 6, 256, 4)])
 def test_tc_filter_refine_matches_exact_kernel(B, C, N, k):
     rng = np.random.default_rng(B * 7 + C + N)
     x = rng.standard_normal((B, C, N)).astype(np.float32)
@@ -175,3 +175,13 @@ def test_tc_filter_refine_on_clustered_dense_and_degenerate_clouds():
     _tc_vs_exact(bad, 10, expect_no_fallback=False)
     big = (1e3 * rng.standard_normal((1, 64, 512))).astype(np.float32)     # large magnitudes (fp16 range of the split)
     _tc_vs_exact(big, 10, expect_no_fallback=False)
+
+
+def test_tc_path_on_the_sphere_template(sphere2048):
+    """EdgeConv1's graph: the xyz sphere (C = 3, zero-padded to 4 channels for the TMA row pitch) through the
+    tensor-core filter + exact refine equals the reference's own list (tests/golden/knn_sphere2048.npz)."""
+    import spgan_b200 as pkg
+    rows = torch.from_numpy(np.tile(sphere2048[None], (2, 1, 1)).astype(np.float32)).cuda().view(-1, 3)
+    got = pkg.ops.knn_indices_rows(rows, 2, 2048, 10).cpu().numpy()
+    want = golden("knn_sphere2048")["idx"].astype(np.int32)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[0])
