@@ -517,14 +517,16 @@ def run_gpu(args, real_stdout):
             pc_bcn = pkg.ops.RowsToBcn.apply(pc_rows, B, 3, N)
             knn2 = ev_ms(lambda: pkg.ops.knn_indices_rows(x1, B, N, G.nk))          # what the generator calls
             knn2_cuda_core = ev_ms(lambda: pkg.ops.knn_indices(x1_bcn, G.nk))
-            knn1 = ev_ms(lambda: pkg.ops.knn_indices(pc_bcn, G.nk))
+            knn1 = ev_ms(lambda: pkg.ops.knn_indices_rows(pc_rows, B, N, G.nk))       # what the generator calls (then caches)
+            knn1_cuda_core = ev_ms(lambda: pkg.ops.knn_indices(pc_bcn, G.nk))
             idx2 = pkg.ops.knn_indices_rows(x1, B, N, G.nk)
-            idx1 = pkg.ops.knn_indices(pc_bcn, G.nk)
+            idx1 = pkg.ops.knn_indices_rows(pc_rows, B, N, G.nk)
             ec2 = ev_ms(lambda: G.EdgeConv2.forward_rows(x1, idx2, B, N))
             ec1 = ev_ms(lambda: G.EdgeConv1.forward_rows(pc_rows, idx1, B, N))
         sub = {"generator_forward_ms_per_batch": g_fwd, "generator_forward_clouds_per_s": B / (g_fwd / 1e3),
                "knn_edgeconv_ms_per_batch": knn1 + knn2 + ec1 + ec2,
-               "knn_C3_ms": knn1, "knn_C64_ms": knn2, "knn_C64_cuda_core_kernel_ms": knn2_cuda_core, "edgeblock1_fwd_ms": ec1, "edgeblock2_fwd_ms": ec2,
+               "knn_C3_ms": knn1, "knn_C3_cuda_core_kernel_ms": knn1_cuda_core, "knn_C64_ms": knn2,
+               "knn_C64_cuda_core_kernel_ms": knn2_cuda_core, "edgeblock1_fwd_ms": ec1, "edgeblock2_fwd_ms": ec2,
                "note": "forward, train-mode BN, B=%d N=%d k=%d; the C=3 graph of the static sphere is cached inside "
                        "training steps (model.py:231) but counted here" % (B, N, G.nk)}
 
