@@ -363,6 +363,35 @@ int spgan_edge_combine(const float *pc, const float *pn, const int32_t *idx, con
  * zeroed by the call). */
 int spgan_edge_combine_bwd(const float *g, const int32_t *idx, int64_t P, int N, int k, int C, float *dpc,
                            float *dpn, spgan_stream_t stream);
+/* EdgeBlock passes with the train-mode BatchNorm reductions folded in (Generator.py:75-88; csrc/edge_fused.cu).
+ * spgan_edge_combine_stats = spgan_edge_combine that ALSO leaves per-column sums / sums of squares of what it writes
+ * as `spgan_edge_stats_rows(P, C)` deterministic partial rows [rows, C] (feed spgan_bn_finalize with R = P*k): the
+ * statistics pass of the BatchNorm2d that follows (Generator.py:58,68) disappears.  out may be NULL (statistics only).
+ * Needs C % 4 == 0, 256 % (C/4) == 0 and 16-byte aligned pointers (else SPGAN_E_UNSUPPORTED; rows() returns 0). */
+size_t spgan_edge_stats_rows(int64_t P, int C);
+int spgan_edge_combine_stats(const float *pc, const float *pn, const int32_t *idx, const float *bias, int64_t P, int N,
+                             int k, int C, float *out, float *col_sum, float *col_sqsum, spgan_stream_t stream);
+/* spgan_bn_softmax_mul_k_bwd that also emits, as `spgan_attn_bwd_rows(P, k, C)` partial rows part[rows, 4, C], the
+ * column sums the two BatchNorm backwards need: (sum g'_w, sum g'_w xhat_w, sum g'_y, sum g'_y xhat_y), g' = the
+ * gradient after the LeakyReLU mask recomputed from xw / xy.  Replaces two spgan_norm_bwd_reduce passes.
+ * 256 % C == 0, k <= 16. */
+size_t spgan_attn_bwd_rows(int64_t P, int k, int C);
+int spgan_bn_softmax_mul_k_bwd_stats(const float *g, const float *xw, const float *xy, const float *w, int64_t P, int k,
+                                     int C, const float *mean_w, const float *rstd_w, const float *gamma_w,
+                                     const float *beta_w, const float *mean_y, const float *rstd_y,
+                                     const float *gamma_y, const float *beta_y, float slope, float *dwa, float *dya,
+                                     float *part, spgan_stream_t stream);
+/* part[rows, nvals, C] -> out[nvals, C]: fixed-tree fp64 sum over the partial rows (deterministic); acc0..acc3
+ * (nullable, [C]) receive += out[v] (parameter gradients accumulated in place).  nvals <= 4. */
+int spgan_partials_finalize(const float *part, int rows, int nvals, int C, float *out, float *acc0, float *acc1,
+                            float *acc2, float *acc3, spgan_stream_t stream);
+/* spgan_edge_combine_bwd applied to dx = gamma rstd (g' - sg/n - xhat sgx/n), n = P*k, formed on the fly from the
+ * gradient g w.r.t. the ACTIVATED tensor and the pre-normalisation tensor x (= spgan_norm_bwd_apply followed by
+ * spgan_edge_combine_bwd without the [P*k, C] intermediate).  C % 4 == 0. */
+int spgan_edge_combine_bwd_bn(const float *g, const float *x, const int32_t *idx, int64_t P, int N, int k, int C,
+                              const float *mean, const float *rstd, const float *gamma, const float *beta,
+                              const float *sg, const float *sgx, float slope, float *dpc, float *dpn,
+                              spgan_stream_t stream);
 /* out[p,c] = max_r x[p,r,c] with argmax (torch.max(x, 3), modules.py:794) and its scatter. */
 int spgan_kmax(const float *x, int64_t P, int k, int C, float *out, int32_t *arg, spgan_stream_t stream);
 int spgan_kmax_scatter(const float *g, const int32_t *arg, int64_t P, int k, int C, float *dx, spgan_stream_t stream);

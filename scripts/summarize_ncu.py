@@ -62,7 +62,7 @@ def main(prefix, reps):
                 else:
                     agg[k] = ls[0][k]
             agg["dram_traffic_bytes"] = agg.get("dram_read", 0.0) + agg.get("dram_write", 0.0)
-            allk[name] = agg
+            allk[name if name not in allk else "%s [%s]" % (name, agg["report"])] = agg
     json.dump(allk, open(prefix + ".json", "w"), indent=1, sort_keys=True)
     with open(prefix + ".md", "w") as f:
         f.write("# ncu --set full summaries (per launch averages; durations are under the profiler: cold, serialised)\n\n")

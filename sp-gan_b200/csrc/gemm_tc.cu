@@ -142,7 +142,7 @@ gemm_tc_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda
     constexpr bool TF32 = cfg::TF32, TWOACC = cfg::TWOACC;
     constexpr int BK = cfg::BK, CHUNK = cfg::CHUNK, ESZ = TF32 ? 4 : 2;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = tc::align_smem_1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
     // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * cfg::STAGES + 4);

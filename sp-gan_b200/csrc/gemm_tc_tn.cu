@@ -62,7 +62,7 @@ gemm_tc_tn_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_
     constexpr int A_TASKS = BM * (BK / 4) / NUM_P_THREADS;     // 2 (row, 4-k chunk) tasks per thread
     constexpr int B_TASKS = BN * (BK / 4) / NUM_P_THREADS;     // 1 / 2 / 4
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = tc::align_smem_1024(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * cfg::STAGES + 2);
     float* epi_smem = reinterpret_cast<float*>(smem + cfg::STAGES * cfg::STAGE_BYTES + 256);

@@ -135,7 +135,7 @@ struct TsParams {
 __global__ void __launch_bounds__(TS_THREADS, 1)
 gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TsParams p) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = tc::align_smem_1024(smem_raw);
     unsigned char* smA = smem;
     unsigned char* smB = smA + A_STAGES * A_STAGE_BYTES;
     float* epi_smem = reinterpret_cast<float*>(smB + B_STAGES * B_STAGE_BYTES);

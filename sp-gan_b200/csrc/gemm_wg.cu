@@ -186,7 +186,7 @@ struct WgParams {
 __global__ void __launch_bounds__(WG_THREADS, 1)
 gemm_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = tc::align_smem_1024(smem_raw);
     unsigned char* stg = smem;                                   // [STAGES][A 32 KB | B 32 KB]
     unsigned char* opb = stg + STAGES * STAGE_BYTES;             // [STAGES][2 column tiles x (hi 8 KB | lo 8 KB)]
     uint64_t* bars = reinterpret_cast<uint64_t*>(opb + STAGES * OPB_BYTES);

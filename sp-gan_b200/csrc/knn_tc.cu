@@ -107,7 +107,7 @@ template <int KLT>                                     // list slots actually ma
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KtParams p) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = tc::align_smem_1024(smem_raw);
     unsigned char* smA = smem;
     unsigned char* smB = smA + A_STAGES * A_STAGE_BYTES;
     float* xch = reinterpret_cast<float*>(smB + B_STAGES * B_STAGE_BYTES);

@@ -9,6 +9,14 @@ constexpr uint32_t SPIN_LIMIT = 1u << 24;      // polls (>= ~60 cycles each): ab
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 1024-byte alignment of the dynamic shared-memory window WITHOUT leaving the shared address space: offsetting the
+// __shared__ array keeps every derived pointer a shared-space pointer (LDS / STS).  Rounding the generic address up
+// through uintptr_t made all of them generic (LD.E / ST.E: long-scoreboard latency, and no reordering across the
+// epilogue's global stores because the compiler had to assume aliasing).
+__device__ __forceinline__ unsigned char* align_smem_1024(unsigned char* raw) {
+    return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -34,6 +42,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // generation: a C-level `if (!wait(...)) return;` makes every loop-carried value of the calling role loop
 // control-dependent on a per-thread predicate, and ptxas then treats the operands of UTCHMMA / UTMALDG as
 // divergent (ELECT / R2UR.BROADCAST loops around every instruction).
+// The exit is made WARP-UNIFORM by a vote: every caller is a converged warp, the barrier address and parity are
+// warp-uniform, and once they live in uniform registers ptxas treats try_wait's predicate as uniform too -- it drops the
+// reconvergence point after the loop and keeps the poll counter in a uniform register.  The hardware does hand
+// different lanes different answers when the phase flips during the poll: lanes that left early then ran a
+// .sync.aligned tcgen05.ld with a partial warp (measured: the tensor-core kNN filter lost neighbours for a few lanes of
+// one warp, ~1 tile in 700).  With the vote all 32 lanes leave on the same poll.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* status) {
     asm volatile(
         "{\n\t"
@@ -42,6 +56,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         "mov.u32 c, 0;\n\t"
         "WAIT_LOOP:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "vote.sync.all.pred p, p, 0xffffffff;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "add.u32 c, c, 1;\n\t"
         "setp.lt.u32 p, c, %3;\n\t"

@@ -105,23 +105,33 @@ class EdgeBlock(nn.Module, _KnnMixin):
         cx, bx, _ = self.conv_x
         # conv_w on the difference half: W (x_j - x_i) + b == (W x)_j - (W x)_i + b
         p1 = ops.linear(x_rows, cw0.weight, engine=0)          # differenced below: exact fp32 products
-        w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))   # [P*k, F/2], pre-BN
+        fuse_w = ops.edge_attention_fusable(bw1, bx, k) and ops.fused_linear_ok(P * k, cw1.weight, bw0, bw1)
         stats_w = None
-        if ops.edge_attention_fusable(bw1, bx, k) and ops.fused_linear_ok(P * k, cw1.weight, bw0, bw1):
-            # BN + LeakyReLU of conv_w[0..2] inside conv_w[3]'s operand converter; the statistics of its output (the
-            # attention logits before their BatchNorm) come out of the same GEMM's epilogue
-            w, st, var_w = ops.bn_act_linear(w, ops.bn_train_stats(w, bw0), bw0, NEG, cw1.weight, cw1.bias, next_bn=bw1,
+        if fuse_w:
+            # the gather kernel leaves conv_w[1]'s batch statistics; BN + LeakyReLU of conv_w[0..2] run inside conv_w[3]'s
+            # operand converter; the statistics of its output (the attention logits before their BatchNorm) come out
+            # of the same GEMM's epilogue
+            if ops.edge_stats_fusable(P, F // 2, bw0):
+                w, st0, _ = ops.edge_combine_bn_stats(None, p1, cw0.bias, idx32, N, k, bw0)      # [P*k, F/2], pre-BN
+            else:
+                w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))
+                st0 = ops.bn_train_stats(w, bw0)
+            w, st, var_w = ops.bn_act_linear(w, st0, bw0, NEG, cw1.weight, cw1.bias, next_bn=bw1,
                                              zero_bias_grad=ops.feeds_train_bn(bw1))
             stats_w = (st[0], st[1], var_w)
         else:
+            w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))   # [P*k, F/2], pre-BN
             w = ops.batch_norm_act(w, bw0, NEG)
             w = ops.linear(w, cw1.weight, cw1.bias, zero_bias_grad=ops.feeds_train_bn(bw1))   # [P*k, F], pre-BN
         # conv_x on [centre, difference]
         a = ops.linear(x_rows, cx.weight, cols=(0, C))
         d = ops.linear(x_rows, cx.weight, engine=0, cols=(C, 2 * C))
-        y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k, ops.feeds_train_bn(bx))   # [P*k, F], pre-BN
-        # BN + LeakyReLU on both branches, softmax over k, then y * w: one fused pass
-        y = ops.bn_act_softmax_mul_k(w, bw1, y, bx, NEG, k, stats_w)
+        if ops.edge_attention_stats_fusable(P, F, k, bw1, bx):
+            # gather + its BatchNorm statistics, then BN + LeakyReLU on both branches, softmax over k and y * w in one pass
+            y = ops.edge_attention(w, stats_w, bw1, a, d, cx.bias, idx32, N, k, bx, NEG)
+        else:
+            y = ops.EdgeCombine.apply(a, d, cx.bias, idx32, N, k, ops.feeds_train_bn(bx))   # [P*k, F], pre-BN
+            y = ops.bn_act_softmax_mul_k(w, bw1, y, bx, NEG, k, stats_w)
         # conv_out: kernel [1, k] == one dense contraction over (neighbour, channel)
         Wo = ops.PermuteOCK.apply(self.conv_out.weight)                         # [F, k*F]
         return ops.Gemm.apply(y.view(P, k * F), Wo, self.conv_out.bias, False, True)

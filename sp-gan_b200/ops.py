@@ -1343,6 +1343,187 @@ class BnActSoftmaxMulKTrain(Function):
 FUSE_EDGE_ATTENTION = _os.environ.get("SPGAN_FUSE_EDGE_ATTENTION", "1") != "0"
 
 
+def _bn_finalize(cs, cq, R, bn_gamma, bn_beta, eps, run, want_tables=True):
+    """Per-CTA column partials (sum, sum of squares) -> (mean, rstd, var, scale, shift) [1, C]; advances the running
+    statistics when `run` = bn_running(bn)."""
+    rows, C = cs.shape
+    dev = cs.device
+    mean = torch.empty((1, C), device=dev, dtype=torch.float32)
+    rstd, var = torch.empty_like(mean), torch.empty_like(mean)
+    scale = torch.empty_like(mean) if want_tables else None
+    shift = torch.empty_like(mean) if want_tables else None
+    L().bn_finalize(cs.data_ptr(), cq.data_ptr(), rows, C, R, float(eps), bn_gamma.data_ptr(), bn_beta.data_ptr(),
+                    mean.data_ptr(), rstd.data_ptr(), var.data_ptr(), scale.data_ptr() if want_tables else None,
+                    shift.data_ptr() if want_tables else None, run[3] if run else 0.0,
+                    run[0].data_ptr() if run else None, run[1].data_ptr() if run else None,
+                    run[2].data_ptr() if run else None, _stream())
+    return mean, rstd, var, scale, shift
+
+
+def _edge_combine_stats(pc, pn, bias, idx, N, k):
+    """spgan_edge_combine_stats -> (out [P*k, C], col_sum, col_sqsum partial rows)."""
+    P, C = pn.shape
+    rows = L().edge_stats_rows(P, C)
+    out = torch.empty((P * k, C), device=pn.device, dtype=torch.float32)
+    cs = torch.empty((rows, C), device=pn.device, dtype=torch.float32)
+    cq = torch.empty_like(cs)
+    L().edge_combine_stats(pc.data_ptr() if pc is not None else None, pn.data_ptr(), idx.data_ptr(),
+                           bias.data_ptr() if bias is not None else None, P, N, k, C, out.data_ptr(), cs.data_ptr(),
+                           cq.data_ptr(), _stream())
+    return out, cs, cq
+
+
+FUSE_EDGE_STATS = _os.environ.get("SPGAN_FUSE_EDGE_STATS", "1") != "0"
+
+
+def edge_stats_fusable(P, C, bn):
+    """Can the edge gather in front of `bn` also produce bn's batch statistics (spgan_edge_combine_stats)?"""
+    return (FUSE_EDGE_STATS and not _TWICE_DIFFERENTIABLE and bn.training and bn.track_running_stats
+            and bn.momentum is not None and L().edge_stats_rows(P, C) != 0)
+
+
+class EdgeCombineStatsTrain(Function):
+    """EdgeCombine in front of a train-mode BatchNorm: the gather kernel also accumulates the column statistics of
+    what it writes, so the BatchNorm's statistics pass over the [P*k, C] tensor disappears (Generator.py:56-58,66-68).
+    Returns (out, mean, rstd, var, scale, shift); the running statistics of the BatchNorm are advanced here."""
+
+    @staticmethod
+    def forward(ctx, pc, pn, bias, idx, N, k, gamma, beta, eps, run):
+        pn = _c(_rows2d(pn))
+        P, C = pn.shape
+        if pc is not None:
+            pc = _c(pc)
+        if bias is not None:
+            bias = _c(bias)
+        out, cs, cq = _edge_combine_stats(pc, pn, bias, idx, N, k)
+        mean, rstd, var, scale, shift = _bn_finalize(cs, cq, P * k, gamma, beta, eps, run)
+        ctx.dims = (P, C, N, k)
+        ctx.has_pc = pc is not None
+        ctx.save_for_backward(idx)
+        ctx.mark_non_differentiable(mean, rstd, var, scale, shift)
+        ctx.set_materialize_grads(False)
+        return out, mean, rstd, var, scale, shift
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, *_unused):
+        (idx,) = ctx.saved_tensors
+        P, C, N, k = ctx.dims
+        if g is None:
+            return (None,) * 10
+        g = _c(g)
+        dpc = torch.empty((P, C), device=g.device, dtype=torch.float32) if (ctx.has_pc and ctx.needs_input_grad[0]) else None
+        dpn = torch.empty((P, C), device=g.device, dtype=torch.float32)
+        L().edge_combine_bwd(g.data_ptr(), idx.data_ptr(), P, N, k, C, dpc.data_ptr() if dpc is not None else None,
+                             dpn.data_ptr(), _stream())
+        # the bias feeds a train-mode BatchNorm: its gradient is exactly zero (column sums of a BN input gradient)
+        return (dpc, dpn) + (None,) * 8
+
+
+def edge_combine_bn_stats(pc, pn, bias, idx, N, k, bn):
+    """-> (pre-BN edge tensor, (mean, rstd, scale, shift), var) for `bn` (train mode; see edge_stats_fusable)."""
+    out, mean, rstd, var, scale, shift = EdgeCombineStatsTrain.apply(pc, pn, bias, idx, N, k, bn.weight, bn.bias, bn.eps,
+                                                                     bn_running(bn))
+    return out, (mean, rstd, scale, shift), var
+
+
+class EdgeAttentionTrain(Function):
+    """EdgeBlock from the per-point conv_x projections to the attention product (Generator.py:66-69,78-82), train mode:
+
+        y    = a[p] + d[nbr] - d[p] + bias_x            (edge gather, its BatchNorm statistics from the same kernel)
+        prod = lrelu(bn_y(y)) * softmax_k(lrelu(bn_w(xw)))
+
+    Backward: ONE pass produces the gradients w.r.t. both activated tensors and the four column sums the two BatchNorm
+    backwards need (no norm_bwd_reduce passes); the conv_x branch's BatchNorm backward is applied inside the scatter
+    of the gather's backward (d y is never written).  Returns prod.  First-order only."""
+
+    @staticmethod
+    def forward(ctx, xw, mean_w, rstd_w, gamma_w, beta_w, a, d, bias_x, idx, N, k, gamma_y, beta_y, eps_y, slope, run_y):
+        xw = _c(_rows2d(xw))
+        a, d = _c(_rows2d(a)), _c(_rows2d(d))
+        E, C = xw.shape
+        P = d.shape[0]
+        if bias_x is not None:
+            bias_x = _c(bias_x)
+        xy, cs, cq = _edge_combine_stats(a, d, bias_x, idx, N, k)
+        mean_y, rstd_y, _, _, _ = _bn_finalize(cs, cq, E, gamma_y, beta_y, eps_y, run_y, want_tables=False)
+        w = torch.empty_like(xw)
+        prod = torch.empty_like(xw)
+        L().bn_softmax_mul_k(xw.data_ptr(), xy.data_ptr(), P, k, C, mean_w.data_ptr(), rstd_w.data_ptr(),
+                             gamma_w.data_ptr(), beta_w.data_ptr(), mean_y.data_ptr(), rstd_y.data_ptr(),
+                             gamma_y.data_ptr(), beta_y.data_ptr(), slope, w.data_ptr(), prod.data_ptr(), _stream())
+        ctx.dims, ctx.slope = (P, C, N, k), slope
+        ctx.save_for_backward(xw, xy, w, idx, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y)
+        ctx.set_materialize_grads(False)
+        return prod
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        xw, xy, w, idx, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y = ctx.saved_tensors
+        if g is None:
+            return (None,) * 16
+        g = _c(g)
+        P, C, N, k = ctx.dims
+        E = P * k
+        dev = g.device
+        rows = L().attn_bwd_rows(P, k, C)
+        part = torch.empty((rows, 4, C), device=dev, dtype=torch.float32)
+        dwa = torch.empty_like(xw)
+        dya = torch.empty_like(xw)
+        L().bn_softmax_mul_k_bwd_stats(g.data_ptr(), xw.data_ptr(), xy.data_ptr(), w.data_ptr(), P, k, C, mean_w.data_ptr(),
+                                       rstd_w.data_ptr(), gamma_w.data_ptr(), beta_w.data_ptr(), mean_y.data_ptr(),
+                                       rstd_y.data_ptr(), gamma_y.data_ptr(), beta_y.data_ptr(), ctx.slope,
+                                       dwa.data_ptr(), dya.data_ptr(), part.data_ptr(), _stream())
+        params_too = not _INPUT_GRAD_ONLY
+        acc_w = params_too and ctx.needs_input_grad[3] and ctx.needs_input_grad[4] and _direct_ok(gamma_w, beta_w)
+        acc_y = params_too and ctx.needs_input_grad[11] and ctx.needs_input_grad[12] and _direct_ok(gamma_y, beta_y)
+        sums = torch.empty((4, C), device=dev, dtype=torch.float32)          # sg_w, sgx_w, sg_y, sgx_y
+        L().partials_finalize(part.data_ptr(), rows, 4, C, sums.data_ptr(),
+                              beta_w.grad.data_ptr() if acc_w else None, gamma_w.grad.data_ptr() if acc_w else None,
+                              beta_y.grad.data_ptr() if acc_y else None, gamma_y.grad.data_ptr() if acc_y else None,
+                              _stream())
+        del part
+        dxw = None
+        if ctx.needs_input_grad[0]:
+            dxw = torch.empty_like(xw)
+            L().norm_bwd_apply(dwa.data_ptr(), xw.data_ptr(), ctx.slope, E, C, E, mean_w.data_ptr(), rstd_w.data_ptr(),
+                               gamma_w.data_ptr(), beta_w.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(),
+                               dxw.data_ptr(), _stream())
+        del dwa
+        da = torch.empty((P, C), device=dev, dtype=torch.float32) if ctx.needs_input_grad[5] else None
+        dd = torch.empty((P, C), device=dev, dtype=torch.float32)
+        L().edge_combine_bwd_bn(dya.data_ptr(), xy.data_ptr(), idx.data_ptr(), P, N, k, C, mean_y.data_ptr(),
+                                rstd_y.data_ptr(), gamma_y.data_ptr(), beta_y.data_ptr(), sums[2].data_ptr(),
+                                sums[3].data_ptr(), ctx.slope, da.data_ptr() if da is not None else None, dd.data_ptr(),
+                                _stream())
+        dgw = dbw = dgy = dby = None
+        if params_too and not acc_w:
+            dgw, dbw = sums[1].clone(), sums[0].clone()
+        if params_too and not acc_y:
+            dgy, dby = sums[3].clone(), sums[2].clone()
+        # bias_x feeds a train-mode BatchNorm: its gradient is exactly zero
+        return (dxw, None, None, dgw, dbw, da, dd, None, None, None, None, dgy, dby, None, None, None)
+
+
+def edge_attention_stats_fusable(P, C, k, bn_w, bn_y):
+    return (edge_attention_fusable(bn_w, bn_y, k) and edge_stats_fusable(P, C, bn_y) and bn_w.momentum is not None
+            and L().attn_bwd_rows(P, k, C) != 0)
+
+
+def edge_attention(xw, stats_w, bn_w, a, d, bias_x, idx, N, k, bn_y, slope):
+    """prod of EdgeAttentionTrain; stats_w = (mean, rstd, var) of xw from its producer, or None (computed here)."""
+    if stats_w is None:
+        xw2 = _c(_rows2d(xw))
+        mean_w, rstd_w, _ = col_stats(xw2.detach(), xw2.shape[0], bn_w.eps, bn_running(bn_w))
+    else:
+        mean_w, rstd_w = stats_w[0], stats_w[1]
+    return EdgeAttentionTrain.apply(xw, mean_w, rstd_w, bn_w.weight, bn_w.bias, a, d, bias_x, idx, N, k, bn_y.weight,
+                                    bn_y.bias, bn_y.eps, slope, bn_running(bn_y))
+
+
+
+
 def edge_attention_fusable(bn_w, bn_y, k):
     return (FUSE_EDGE_ATTENTION and k <= 16 and bn_w.training and bn_y.training and bn_w.track_running_stats
             and bn_y.track_running_stats and not _TWICE_DIFFERENTIABLE)
