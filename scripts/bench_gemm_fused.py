@@ -31,7 +31,7 @@ for M, N, K in [(131072, 1024, 256), (131072, 256, 128), (131072, 128, 256), (13
     t1 = med(lambda: ops.gemm_raw(A, B, None, False, True, out=out, engine=1))
     t3 = med(lambda: ops.gemm_raw(A, B, None, False, True, out=out, engine=3))
     tf = med(lambda: ops.gemm_fused_raw(A, B, None, tb=True, out=out))
-    tfs = med(lambda: ops.gemm_fused_raw(A, B, None, tb=True, out=out, a_scale=sc, a_shift=sh, a_slope=0.01, want_stats=True))
+    tfs = med(lambda: ops.gemm_fused_raw(A, B, None, tb=True, out=out, a_scale=sc, a_shift=sh, a_slope=0.01, want_stats=N <= 256))
     fl = 2.0 * M * N * K / 1e9
     byts = 4.0 * M * (N + K) / 1e6
     print("M=%-8d N=%-5d K=%-4d  tf32x3 %.3f ms (%5.1f TF)  engine3 %.3f ms (%5.1f TF)  fused %.3f ms (%5.1f TF, %5.2f TB/s)  "

@@ -77,6 +77,28 @@ def test_fused_prologue_stats_accumulate(M, N, K):
     assert torch.equal(out2, out3)
 
 
+@pytest.mark.parametrize("M,N,K", [(131072, 1024, 256), (1310720, 64, 128), (1310720, 128, 64), (131072, 256, 128),
+                                   (131072, 192, 64), (1310720, 32, 64), (200000, 320, 256)])
+def test_fused_pipeline_under_repetition_on_the_step_shapes(M, N, K):
+    """The warp-specialised pipeline (TMA producers, converters, MMA issuer, epilogue) on the
+    training step's own shapes -- many row tiles per CTA, 1 / 2 / 3 / 5 / 16 column tiles, every K-block count -- launched
+    back to back: a protocol slip shows up as a pipeline time-out (trap) or a wrong tile, whatever the timing."""
+    ops = _ops()
+    A = _rnd(4096, K, seed=5).cuda().repeat(M // 4096 + 1, 1)[:M].contiguous()
+    B = _rnd(N, K, seed=6).cuda()
+    ref = (A[:4096].double() @ B.double().t()).float()
+    out = torch.empty((M, N), device="cuda")
+    for _ in range(60):
+        assert ops.gemm_fused_raw(A, B, None, tb=True, out=out, wcache=False) is not None
+    assert _status(ops) == 0
+    for r0 in (0, (M // 4096 - 1) * 4096, (M // 8192) * 4096):
+        emax, el2 = rel_err(out[r0:r0 + 4096].cpu().numpy(), ref.cpu().numpy())
+        assert emax < 1e-5 and el2 < 2e-6, (r0, emax, el2)
+    first = out.clone()
+    ops.gemm_fused_raw(A, B, None, tb=True, out=out, wcache=False)
+    assert torch.equal(first, out), "same operands, same result bit for bit"
+
+
 def test_fused_strided_operands_and_unsupported_shapes():
     ops = _ops()
     big = _rnd(5000, 256, seed=9).cuda()
