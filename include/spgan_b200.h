@@ -179,6 +179,16 @@ size_t spgan_gemm_workspace(int engine, int N, int K);
  * (deterministic; the engine-1 kernel, taken for shapes / alignments outside gemm_wg.cu's envelope or when the
  * workspace is smaller, flushes with atomics).  The status word is written only by a pipeline timeout, which traps. */
 size_t spgan_gemm_wgrad_workspace(int64_t Mo, int No, int64_t K);
+/* Weight gradient with the forward's operand prologue folded in:  C[Mo,No] (+)= dY^T * pro(X),
+ * pro(x)[k,n] = LeakyReLU_slope(x[k,n] * x_scale[n] + x_shift[n]) (both NULL: identity), dY [K,Mo], X [K,No] row-major
+ * fp32, K = points / edges.  The weight gradient of conv(LeakyReLU(BatchNorm(x))) (Generator.py:56-62,
+ * Discriminator.py:55-81 under autograd) needs the ACTIVATED input, which spgan_gemm_fused never wrote: it is re-formed
+ * inside the converter of the tcgen05 weight-gradient kernel instead of by a spgan_norm_apply pass.  Engine-3 arithmetic,
+ * deterministic split-K partials; workspace = spgan_gemm_wgrad_workspace bytes, 256-byte aligned.
+ * SPGAN_E_UNSUPPORTED outside the kernel's envelope (Mo, No >= 16, K >= 4096, ld % 4 == 0, 16-byte aligned). */
+int spgan_gemm_wgrad_fused(int64_t Mo, int No, int64_t K, const float *dY, int64_t ldy, const float *X, int64_t ldx,
+                           const float *x_scale, const float *x_shift, float x_slope, float *C, int64_t ldc,
+                           int accumulate, void *workspace, size_t workspace_bytes, spgan_stream_t stream);
 int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float *A, int64_t lda, const float *B,
                int64_t ldb, float *C, int64_t ldc, const float *bias, int accumulate, int engine, void *workspace,
                size_t workspace_bytes, spgan_stream_t stream);
@@ -334,6 +344,7 @@ int spgan_softmax_k_bwd(const float *g, const float *y, int64_t P, int k, int C,
  * w = softmax_k(lrelu(bn_w(xw))), prod = lrelu(bn_y(xy)) * w from the PRE-normalisation tensors xw, xy [P, k, C]
  * and per-channel (mean, rstd, gamma, beta) of the two BatchNorm2d layers; bit-identical to
  * spgan_norm_apply x2 + spgan_softmax_mul_k without writing the normalised tensors.  k <= 16.
+ * w may be NULL (no backward pass will follow: the softmax weights are not written).
  * Backward: dwa / dya = gradients w.r.t. the two ACTIVATED tensors (feed spgan_norm_bwd_*); either may be NULL. */
 int spgan_bn_softmax_mul_k(const float *xw, const float *xy, int64_t P, int k, int C, const float *mean_w,
                            const float *rstd_w, const float *gamma_w, const float *beta_w, const float *mean_y,

@@ -298,7 +298,8 @@ int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t l
 bool spgan_gemm_wg_supported(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb);
 size_t spgan_gemm_wg_workspace(int64_t Mo, int No, int64_t K);
 int spgan_gemm_wg(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
-                  int64_t ldc, int accumulate, void* workspace, cudaStream_t st);
+                  int64_t ldc, int accumulate, void* workspace, cudaStream_t st, const float* b_scale, const float* b_shift,
+                  float b_slope);
 static bool wg_enabled() {
     static const bool on = [] { const char* e = getenv("SPGAN_WG"); return !(e && e[0] == '0'); }();
     return on;
@@ -348,7 +349,7 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
     if (engine == 3 && workspace != nullptr && transA && !transB && bias == nullptr && wg_enabled() &&
         (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && spgan_gemm_wg_supported(M, N, K, A, lda, B, ldb) &&
         workspace_bytes >= spgan_gemm_wg_workspace(M, N, K))
-        return spgan_gemm_wg(M, N, K, A, lda, B, ldb, C, ldc, accumulate, workspace, as_stream(stream));
+        return spgan_gemm_wg(M, N, K, A, lda, B, ldb, C, ldc, accumulate, workspace, as_stream(stream), nullptr, nullptr, 1.f);
     if (engine == 3) engine = 1;          // otherwise the TF32x3 transposing kernel for every tensor engine
     // weight gradients, first generation (TF32x3, atomic flush)
     if ((engine == 1 || engine == 2) && workspace != nullptr && workspace_bytes >= 256 && transA && !transB &&
@@ -391,4 +392,17 @@ extern "C" int spgan_gemm_fused(int transB, int64_t M, int N, int K, const float
 extern "C" size_t spgan_gemm_wgrad_workspace(int64_t Mo, int No, int64_t K) {
     if (Mo < 1 || No < 1 || K < 1) return 256;
     return spgan_gemm_wg_workspace(Mo, No, K);
+}
+
+extern "C" int spgan_gemm_wgrad_fused(int64_t Mo, int No, int64_t K, const float* dY, int64_t ldy, const float* X,
+                                      int64_t ldx, const float* x_scale, const float* x_shift, float x_slope, float* C,
+                                      int64_t ldc, int accumulate, void* workspace, size_t workspace_bytes,
+                                      spgan_stream_t stream) {
+    SPGAN_CHECK_ARG(dY && X && C && Mo >= 1 && No >= 1 && K >= 1 && ldy >= Mo && ldx >= No && ldc >= No);
+    SPGAN_CHECK_ARG((x_scale == nullptr) == (x_shift == nullptr) && x_slope > 0.f && x_slope <= 1.f);
+    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || !wg_enabled() ||
+        !spgan_gemm_wg_supported(Mo, No, K, dY, ldy, X, ldx) || workspace_bytes < spgan_gemm_wg_workspace(Mo, No, K))
+        return SPGAN_E_UNSUPPORTED;
+    return spgan_gemm_wg(Mo, No, K, dY, ldy, X, ldx, C, ldc, accumulate, workspace, as_stream(stream), x_scale, x_shift,
+                         x_slope);
 }

@@ -181,6 +181,9 @@ struct WgParams {
     int64_t rows_per_chunk;          // multiple of BK
     float* partial;                  // [k_chunks, Mo, No]
     int* status;
+    const float* b_scale;            // prologue of the B operand, per channel n (both NULL: identity):
+    const float* b_shift;            //   B'[k, n] = LeakyReLU_slope(B[k, n] * b_scale[n] + b_shift[n])
+    float b_slope;
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -331,6 +334,19 @@ gemm_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bw = warp - B_WARP0;                      // 0..7
         int stage = 0;
         uint32_t phase = 0;
+        // Prologue (the BatchNorm + LeakyReLU the forward applied to this operand inside its GEMM, BnActLinearTrain):
+        // the activated input of a weight gradient is formed here, in the converter, instead of by a norm_apply pass
+        // that writes it to HBM for this kernel to read back.  A thread's four tasks are the channels j * 32 + lane.
+        // (Rows beyond K are zero-filled in BOTH operands; dY = 0 there, so what the prologue makes of them is moot.)
+        const bool has_pro = p.b_scale != nullptr;
+        const float slope = p.b_slope;
+        float psc[4], psh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + j * 32 + lane;
+            psc[j] = (has_pro && gn < p.No) ? __ldg(p.b_scale + gn) : 0.f;
+            psh[j] = (has_pro && gn < p.No) ? __ldg(p.b_shift + gn) : 0.f;
+        }
         for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(bar(BAR_S_FULL + stage), phase, vstatus);
             const unsigned char* tileB = stg + stage * STAGE_BYTES + SA_BYTES;
@@ -344,8 +360,14 @@ gemm_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if ((n >> 6) >= nt) continue;                       // (warp-uniform) column tile not in this CTA
                 uint32_t hh[4], ll[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    split2_f16s(staged(tileB, c * 8 + 2 * e, n), staged(tileB, c * 8 + 2 * e + 1, n), hh[e], ll[e]);
+                for (int e = 0; e < 4; ++e) {
+                    float x0 = staged(tileB, c * 8 + 2 * e, n), x1 = staged(tileB, c * 8 + 2 * e + 1, n);
+                    if (has_pro) {                                   // same expression as gemm_ts.cu's converter
+                        x0 = fmaf(x0, psc[j], psh[j]); x0 = fmaxf(x0, x0 * slope);
+                        x1 = fmaf(x1, psc[j], psh[j]); x1 = fmaxf(x1, x1 * slope);
+                    }
+                    split2_f16s(x0, x1, hh[e], ll[e]);
+                }
                 vhi[j] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                 vlo[j] = make_uint4(ll[0], ll[1], ll[2], ll[3]);
             }
@@ -437,7 +459,8 @@ size_t spgan_gemm_wg_workspace(int64_t Mo, int No, int64_t K) {
 }
 
 int spgan_gemm_wg(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
-                  int64_t ldc, int accumulate, void* workspace, cudaStream_t st) {
+                  int64_t ldc, int accumulate, void* workspace, cudaStream_t st, const float* b_scale, const float* b_shift,
+                  float b_slope) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (enc == nullptr) return SPGAN_E_UNSUPPORTED;
     const WgPlan pl = make_plan(Mo, No, K);
@@ -466,6 +489,7 @@ int spgan_gemm_wg(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, co
     p.m_tiles = pl.m_tiles; p.n_groups = pl.n_groups; p.k_chunks = pl.k_chunks; p.rows_per_chunk = pl.rows_per_chunk;
     p.partial = reinterpret_cast<float*>(ws + 256);
     p.status = reinterpret_cast<int*>(ws);
+    p.b_scale = b_scale; p.b_shift = b_shift; p.b_slope = b_slope;
     cudaError_t e = cudaFuncSetAttribute(gemm_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     const int grid = pl.m_tiles * pl.n_groups * pl.k_chunks;

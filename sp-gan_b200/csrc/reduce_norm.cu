@@ -749,7 +749,7 @@ bn_softmax_mul_k_kernel(const float* __restrict__ xw, const float* __restrict__ 
         for (int r = 0; r < KM; ++r)
             if (r < k) {
                 const float wr = a[r] * inv;
-                w[o + (int64_t)r * C] = wr;
+                if (w) w[o + (int64_t)r * C] = wr;               // the softmax weights are only kept for a backward pass
                 prod[o + (int64_t)r * C] = wr * bn_act(b[r], my, ry, gy, bby, slope);
             }
     }
@@ -1281,7 +1281,7 @@ extern "C" int spgan_bn_softmax_mul_k(const float* xw, const float* xy, int64_t 
                                       const float* rstd_w, const float* gamma_w, const float* beta_w,
                                       const float* mean_y, const float* rstd_y, const float* gamma_y,
                                       const float* beta_y, float slope, float* w, float* prod, spgan_stream_t s) {
-    SPGAN_CHECK_ARG(xw && xy && w && prod && mean_w && rstd_w && gamma_w && beta_w && mean_y && rstd_y && gamma_y && beta_y);
+    SPGAN_CHECK_ARG(xw && xy && prod && mean_w && rstd_w && gamma_w && beta_w && mean_y && rstd_y && gamma_y && beta_y);
     SPGAN_CHECK_ARG(P >= 0 && k >= 1 && C >= 1);
     if (k > KMAXR) return SPGAN_E_UNSUPPORTED;
     if (P == 0) return SPGAN_OK;

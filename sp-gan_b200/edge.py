@@ -112,12 +112,14 @@ class EdgeBlock(nn.Module, _KnnMixin):
             # operand converter; the statistics of its output (the attention logits before their BatchNorm) come out
             # of the same GEMM's epilogue
             if ops.edge_stats_fusable(P, F // 2, bw0):
-                w, st0, _ = ops.edge_combine_bn_stats(None, p1, cw0.bias, idx32, N, k, bw0)      # [P*k, F/2], pre-BN
+                # gather + conv_w[1..3] as one node: see ops.EdgeGatherBnActLinearTrain
+                w, st, var_w = ops.edge_gather_bn_act_linear(p1, cw0.bias, idx32, N, k, bw0, cw1.weight, cw1.bias, NEG, bw1,
+                                                             ops.feeds_train_bn(bw1))
             else:
                 w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))
                 st0 = ops.bn_train_stats(w, bw0)
-            w, st, var_w = ops.bn_act_linear(w, st0, bw0, NEG, cw1.weight, cw1.bias, next_bn=bw1,
-                                             zero_bias_grad=ops.feeds_train_bn(bw1))
+                w, st, var_w = ops.bn_act_linear(w, st0, bw0, NEG, cw1.weight, cw1.bias, next_bn=bw1,
+                                                 zero_bias_grad=ops.feeds_train_bn(bw1))
             stats_w = (st[0], st[1], var_w)
         else:
             w = ops.EdgeCombine.apply(None, p1, cw0.bias, idx32, N, k, ops.feeds_train_bn(bw0))   # [P*k, F/2], pre-BN

@@ -883,6 +883,34 @@ class BatchNormActSegMaxTrain(Function):
         return dx, sgx, sg, None, None, None
 
 
+FUSE_WGRAD_PROLOGUE = _os.environ.get("SPGAN_FUSE_WGRAD_PROLOGUE", "1") != "0"
+
+
+def wgrad_bn_act(gz, x_pre, scale, shift, slope, mean, rstd, gamma, beta, W, direct):
+    """dW of z = lrelu(bn(x_pre)) @ W^T: gz^T @ lrelu(x_pre * scale + shift).  The activated input is re-formed inside
+    the weight-gradient kernel's operand converter (spgan_gemm_wgrad_fused); outside that kernel's envelope it is
+    recomputed by a norm_apply pass first.  direct: accumulate into W.grad (returns None), else returns dW."""
+    R, K = x_pre.shape
+    Cout = gz.shape[1]
+    out = _wmat(W.grad, None) if direct else torch.empty((Cout, K), device=gz.device, dtype=torch.float32)
+    if (FUSE_WGRAD_PROLOGUE and GEMM_ENGINE == 3 and R >= 4096 and 16 <= Cout <= 65536 and K >= 16 and 0.0 < slope <= 1.0
+            and gz.stride(0) % 4 == 0 and x_pre.stride(0) % 4 == 0 and gz.data_ptr() % 16 == 0 and x_pre.data_ptr() % 16 == 0
+            and gz.stride(1) == 1 and x_pre.stride(1) == 1):
+        global LAST_TC_WORKSPACE
+        ws_bytes = L().gemm_wgrad_workspace(Cout, K, R)
+        ws = torch.empty(ws_bytes // 4, device=gz.device, dtype=torch.float32)
+        LAST_TC_WORKSPACE = ws
+        L().gemm_wgrad_fused(Cout, K, R, gz.data_ptr(), gz.stride(0), x_pre.data_ptr(), x_pre.stride(0), scale.data_ptr(),
+                             shift.data_ptr(), float(slope), out.data_ptr(), out.stride(0), int(direct), ws.data_ptr(),
+                             ws_bytes, _stream())
+    else:
+        a = torch.empty_like(x_pre)                       # recompute the activated input for the weight gradient
+        L().norm_apply(x_pre.data_ptr(), R, K, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                       slope, a.data_ptr(), _stream())
+        gemm_raw(gz, a, None, True, False, out=out, accumulate=direct)
+    return None if direct else out.reshape(W.shape)
+
+
 class BnActLinearTrain(Function):
     """z = LeakyReLU(BatchNorm_train(x_pre)) @ W^T + b in ONE pass over x_pre (spgan_gemm_fused): the normalised,
     activated tensor never reaches HBM -- it is formed in the GEMM's A-operand converter -- and, with `next_bn`, the
@@ -903,7 +931,7 @@ class BnActLinearTrain(Function):
         if res is None:
             raise RuntimeError("BnActLinearTrain: shape outside spgan_gemm_fused's envelope (caller must check fused_linear_ok)")
         ctx.slope, ctx.zero_bias_grad, ctx.has_bias = slope, zero_bias_grad, bias is not None
-        ctx.save_for_backward(x_pre, mean, rstd, gamma, beta, W)
+        ctx.save_for_backward(x_pre, mean, rstd, gamma, beta, W, scale, shift)
         ctx.set_materialize_grads(False)
         if not want:
             return res
@@ -923,7 +951,7 @@ class BnActLinearTrain(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gz, *_unused):
-        x_pre, mean, rstd, gamma, beta, W = ctx.saved_tensors
+        x_pre, mean, rstd, gamma, beta, W, scale, shift = ctx.saved_tensors
         if gz is None:
             return (None,) * 12
         gz = _c(gz)
@@ -932,14 +960,7 @@ class BnActLinearTrain(Function):
         dW = db = dgamma = dbeta = dx = None
         params_too = not _INPUT_GRAD_ONLY
         if ctx.needs_input_grad[7] and params_too:
-            a = torch.empty_like(x_pre)                       # recompute the activated input for the weight gradient
-            L().norm_apply(x_pre.data_ptr(), R, K, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                           ctx.slope, a.data_ptr(), _stream())
-            if _direct_ok(W):
-                gemm_raw(gz, a, None, True, False, out=_wmat(W.grad, None), accumulate=True)
-            else:
-                dW = gemm_raw(gz, a, None, True, False).reshape(W.shape)
-            del a
+            dW = wgrad_bn_act(gz, x_pre, scale, shift, ctx.slope, mean, rstd, gamma, beta, W, _direct_ok(W))
         if ctx.has_bias and ctx.needs_input_grad[8] and params_too and not ctx.zero_bias_grad:
             db = ColSum.apply(gz, R).view(-1)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
@@ -1420,6 +1441,85 @@ class EdgeCombineStatsTrain(Function):
         return (dpc, dpn) + (None,) * 8
 
 
+class EdgeGatherBnActLinearTrain(Function):
+    """conv_w of EdgeBlock as ONE node (Generator.py:56-62,78), train mode, first order:
+
+        w0 = p1[nbr] - p1[p] + b0                (edge gather; BatchNorm statistics from the same kernel)
+        z  = lrelu(bn0(w0)) @ W^T + b            (BN + LeakyReLU in the GEMM's operand converter; statistics of z, the
+                                                  next BatchNorm's input, from its epilogue)
+
+    Backward: the weight gradient re-forms the activated operand inside its own converter (no norm_apply pass), and the
+    BatchNorm backward of bn0 is applied inside the scatter of the gather's backward (d w0 is never written).
+    Returns (z, mean_z, rstd_z, var_z, scale_z, shift_z)."""
+
+    @staticmethod
+    def forward(ctx, p1, bias0, idx, N, k, gamma0, beta0, eps0, run0, W, bias, slope, next_bn, zero_bias_grad):
+        p1 = _c(_rows2d(p1))
+        P, C0 = p1.shape
+        if bias0 is not None:
+            bias0 = _c(bias0)
+        w0, cs, cq = _edge_combine_stats(None, p1, bias0, idx, N, k)
+        E = P * k
+        mean0, rstd0, _, scale0, shift0 = _bn_finalize(cs, cq, E, gamma0, beta0, eps0, run0)
+        res = gemm_fused_raw(w0, _wmat(W, None), bias, tb=True, a_scale=scale0, a_shift=shift0, a_slope=slope,
+                             want_stats=True, wcache=True)
+        if res is None:
+            raise RuntimeError("EdgeGatherBnActLinearTrain: shape outside spgan_gemm_fused's envelope")
+        z, cs2, cq2 = res
+        m2, r2, v2, sc2, sh2 = _bn_finalize(cs2, cq2, E, next_bn.weight, next_bn.bias, next_bn.eps, bn_running(next_bn))
+        ctx.dims, ctx.slope, ctx.has_bias, ctx.zero_bias_grad = (P, C0, N, k), slope, bias is not None, zero_bias_grad
+        ctx.mark_non_differentiable(m2, r2, v2, sc2, sh2)
+        ctx.set_materialize_grads(False)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(w0, idx, mean0, rstd0, gamma0, beta0, scale0, shift0, W)
+        return z, m2, r2, v2, sc2, sh2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz, *_unused):
+        if gz is None:
+            return (None,) * 14
+        w0, idx, mean0, rstd0, gamma0, beta0, scale0, shift0, W = ctx.saved_tensors
+        P, C0, N, k = ctx.dims
+        E = P * k
+        gz = _c(gz)
+        params_too = not _INPUT_GRAD_ONLY
+        dW = db = dgamma = dbeta = dp1 = None
+        if ctx.needs_input_grad[9] and params_too:
+            dW = wgrad_bn_act(gz, w0, scale0, shift0, ctx.slope, mean0, rstd0, gamma0, beta0, W, _direct_ok(W))
+        if ctx.has_bias and ctx.needs_input_grad[10] and params_too and not ctx.zero_bias_grad:
+            db = ColSum.apply(gz, E).view(-1)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+            ga = gemm_raw(gz, _wmat(W, None), None, False, False, wcache=True)         # d(activated w0)
+            acc = params_too and ctx.needs_input_grad[5] and ctx.needs_input_grad[6] and _direct_ok(gamma0, beta0)
+            sg = torch.empty((1, C0), device=ga.device, dtype=torch.float32)
+            sgx = torch.empty_like(sg)
+            ws = _ws(E, C0, E, 2, ga.device)
+            if acc:
+                L().norm_bwd_reduce_acc(ga.data_ptr(), w0.data_ptr(), ctx.slope, E, C0, mean0.data_ptr(), rstd0.data_ptr(),
+                                        gamma0.data_ptr(), beta0.data_ptr(), sg.data_ptr(), sgx.data_ptr(),
+                                        beta0.grad.data_ptr(), gamma0.grad.data_ptr(), ws.data_ptr(), _stream())
+            else:
+                L().norm_bwd_reduce(ga.data_ptr(), w0.data_ptr(), ctx.slope, E, C0, E, mean0.data_ptr(), rstd0.data_ptr(),
+                                    gamma0.data_ptr(), beta0.data_ptr(), sg.data_ptr(), sgx.data_ptr(), ws.data_ptr(), _stream())
+                if params_too:
+                    dgamma, dbeta = sgx.view(-1), sg.view(-1)
+            if ctx.needs_input_grad[0]:
+                dp1 = torch.empty((P, C0), device=ga.device, dtype=torch.float32)
+                L().edge_combine_bwd_bn(ga.data_ptr(), w0.data_ptr(), idx.data_ptr(), P, N, k, C0, mean0.data_ptr(),
+                                        rstd0.data_ptr(), gamma0.data_ptr(), beta0.data_ptr(), sg.data_ptr(), sgx.data_ptr(),
+                                        ctx.slope, None, dp1.data_ptr(), _stream())
+        # bias0 feeds a train-mode BatchNorm: exactly zero gradient
+        return dp1, None, None, None, None, dgamma, dbeta, None, None, dW, db, None, None, None
+
+
+def edge_gather_bn_act_linear(p1, bias0, idx, N, k, bn0, weight, bias, slope, next_bn, zero_bias_grad):
+    """-> (z, (mean, rstd, scale, shift) of z, var of z): see EdgeGatherBnActLinearTrain."""
+    z, m2, r2, v2, sc2, sh2 = EdgeGatherBnActLinearTrain.apply(p1, bias0, idx, N, k, bn0.weight, bn0.bias, bn0.eps,
+                                                              bn_running(bn0), weight, bias, slope, next_bn, zero_bias_grad)
+    return z, (m2, r2, sc2, sh2), v2
+
+
 def edge_combine_bn_stats(pc, pn, bias, idx, N, k, bn):
     """-> (pre-BN edge tensor, (mean, rstd, scale, shift), var) for `bn` (train mode; see edge_stats_fusable)."""
     out, mean, rstd, var, scale, shift = EdgeCombineStatsTrain.apply(pc, pn, bias, idx, N, k, bn.weight, bn.bias, bn.eps,
@@ -1447,12 +1547,18 @@ class EdgeAttentionTrain(Function):
             bias_x = _c(bias_x)
         xy, cs, cq = _edge_combine_stats(a, d, bias_x, idx, N, k)
         mean_y, rstd_y, _, _, _ = _bn_finalize(cs, cq, E, gamma_y, beta_y, eps_y, run_y, want_tables=False)
-        w = torch.empty_like(xw)
+        # the softmax weights are kept for the backward pass only: a no-grad forward (the critic phase's generator
+        # pass, model.py:246-248) does not write them
+        need_bwd = any(ctx.needs_input_grad)
+        w = torch.empty_like(xw) if need_bwd else None
         prod = torch.empty_like(xw)
         L().bn_softmax_mul_k(xw.data_ptr(), xy.data_ptr(), P, k, C, mean_w.data_ptr(), rstd_w.data_ptr(),
                              gamma_w.data_ptr(), beta_w.data_ptr(), mean_y.data_ptr(), rstd_y.data_ptr(),
-                             gamma_y.data_ptr(), beta_y.data_ptr(), slope, w.data_ptr(), prod.data_ptr(), _stream())
+                             gamma_y.data_ptr(), beta_y.data_ptr(), slope, w.data_ptr() if need_bwd else None,
+                             prod.data_ptr(), _stream())
         ctx.dims, ctx.slope = (P, C, N, k), slope
+        if not need_bwd:
+            return prod
         ctx.save_for_backward(xw, xy, w, idx, gamma_w, beta_w, gamma_y, beta_y, mean_w, rstd_w, mean_y, rstd_y)
         ctx.set_materialize_grads(False)
         return prod

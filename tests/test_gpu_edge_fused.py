@@ -203,6 +203,9 @@ def test_edge_block_fused_equals_unfused():
                           fwd_launches)
     finally:
         (ops.FUSE_EDGE_STATS,) = saved
+    with torch.no_grad():                       # the critic phase's generator pass: no softmax weights are written
+        out_ng = blk(x0.clone(), idx)
+    assert torch.equal(out_ng, res[True][0]), "no-grad forward must equal the recorded one bit for bit"
     close(res[True][0], res[False][0], 2e-5, "forward")
     close(res[True][1], res[False][1], 5e-4, "input gradient")
     scale = max(float(v.abs().max()) for v in res[False][2].values())

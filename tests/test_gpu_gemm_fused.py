@@ -188,6 +188,42 @@ def test_wgrad_engine3_matches_fp64_and_is_deterministic(Mo, No, K):
     assert float(wide[:, :4].min()) == 1.0 and float(wide[:, 4 + No:].max()) == 1.0
 
 
+@pytest.mark.parametrize("Mo,No,K", [(1024, 256, 131072), (128, 64, 400000), (256, 128, 40004), (64, 32, 50000),
+                                     (72, 100, 9004), (16, 16, 4096)])
+def test_wgrad_with_operand_prologue_matches_fp64(Mo, No, K):
+    """spgan_gemm_wgrad_fused: C = dY^T lrelu(X * scale + shift), the activated operand formed inside the kernel's
+    converter -- against the fp64 product of the explicitly activated operand, and through ops.wgrad_bn_act (both the
+    in-kernel prologue and the norm_apply fallback give the same weight gradient)."""
+    ops = _ops()
+    L = ops.L()
+    gz, x = _rnd(K, Mo, seed=21).cuda(), (_rnd(K, No, seed=22) * 1.3 + 0.2).cuda()
+    sc, sh = (torch.rand(No) + 0.5).cuda(), (_rnd(No, seed=23) * 0.4).cuda()
+    slope = 0.01
+    act = torch.nn.functional.leaky_relu(x.double().cpu() * sc.double().cpu() + sh.double().cpu(), slope)
+    ref = gz.double().cpu().t() @ act
+    ws_bytes = L.gemm_wgrad_workspace(Mo, No, K)
+    ws = torch.empty(ws_bytes // 4, device="cuda")
+    out = torch.full((Mo, No), 3.0, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.gemm_wgrad_fused(Mo, No, K, gz.data_ptr(), Mo, x.data_ptr(), No, sc.data_ptr(), sh.data_ptr(), slope, out.data_ptr(), No, 0,
+                       ws.data_ptr(), ws_bytes, st)
+    torch.cuda.synchronize()                     # (a pipeline time-out traps: it would surface here)
+    emax, el2 = rel_err(out.cpu().numpy(), ref.numpy())
+    assert emax < 4e-5 and el2 < 8e-6, (emax, el2)
+    out2 = torch.empty_like(out)
+    L.gemm_wgrad_fused(Mo, No, K, gz.data_ptr(), Mo, x.data_ptr(), No, sc.data_ptr(), sh.data_ptr(), slope, out2.data_ptr(), No, 0,
+                       ws.data_ptr(), ws_bytes, st)
+    assert torch.equal(out, out2), "deterministic"
+    L.gemm_wgrad_fused(Mo, No, K, gz.data_ptr(), Mo, x.data_ptr(), No, sc.data_ptr(), sh.data_ptr(), slope, out2.data_ptr(), No, 1,
+                       ws.data_ptr(), ws_bytes, st)
+    emax, _ = rel_err(out2.cpu().numpy(), 2 * ref.numpy())
+    assert emax < 8e-5, emax
+    # identity prologue == the plain weight gradient
+    L.gemm_wgrad_fused(Mo, No, K, gz.data_ptr(), Mo, x.data_ptr(), No, None, None, 1.0, out2.data_ptr(), No, 0, ws.data_ptr(),
+                       ws_bytes, st)
+    assert torch.equal(out2, ops.gemm_raw(gz, x, None, True, False, engine=3))
+
+
 def test_split_weight_cache_follows_the_parameter():
     """The split (fp16 hi / lo) of a Parameter is kept across products until the parameter changes: in-place updates
     bump its version, raw-pointer updates announce themselves through ops.weights_changed()."""
