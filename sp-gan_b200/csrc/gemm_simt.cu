@@ -314,6 +314,9 @@ bool spgan_gemm_tc_tn_supported(int64_t Mo, int No, int64_t K, const float* A, i
 int spgan_gemm_tc_tn(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                      int64_t ldc, int accumulate, void* workspace, cudaStream_t st);
 
+bool spgan_gemm_thin_supported(int transA, int64_t M, int N, int K, const float* A, int64_t lda);
+int spgan_gemm_thin(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
+                    int64_t ldc, const float* bias, int accumulate, cudaStream_t st);
 bool spgan_gemm_tn_skinny_supported(int64_t Mo, int No, int64_t K);
 int spgan_gemm_tn_skinny(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
                          float* C, int64_t ldc, int accumulate, cudaStream_t st);
@@ -359,6 +362,9 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
     // tall-skinny weight gradients (tiny output, K = #points / #edges): stream K once (any engine)
     if (transA && !transB && bias == nullptr && spgan_gemm_tn_skinny_supported(M, N, K))
         return spgan_gemm_tn_skinny(M, N, K, A, lda, B, ldb, C, ldc, accumulate, as_stream(stream));
+    // thin products (K <= 8 or N <= 4 over >= 4096 rows): streaming kernels, exact fp32 (any engine)
+    if (spgan_gemm_thin_supported(transA, M, N, K, A, lda))
+        return spgan_gemm_thin(transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream));
     return spgan_gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, as_stream(stream),
                            workspace, workspace_bytes);
 }

@@ -107,8 +107,14 @@ class AdaptivePointNorm(nn.Module):
         self.style.bias.data[:in_channel] = 1
         self.style.bias.data[in_channel:] = 0
 
-    def forward_rows(self, x_rows, style_rows, N):
-        s = ops.linear(style_rows, self.style.weight, self.style.bias)          # [P, 2C]
+    def forward_rows(self, x_rows, style_rows, N, style_slope=None):
+        """style_slope: the style rows are PRE-activation values of the generator head and LeakyReLU(style_slope) is
+        still to be applied -- it is, inside the style conv's GEMM (ops.act_linear), so the activated style tensor is
+        never written."""
+        if style_slope is None:
+            s = ops.linear(style_rows, self.style.weight, self.style.bias)          # [P, 2C]
+        else:
+            s = ops.act_linear(style_rows, style_slope, self.style.weight, self.style.bias)
         return ops.AdaIN.apply(x_rows, s, N, self.norm.eps)
 
     def forward(self, input, style):
@@ -169,8 +175,9 @@ class Generator(nn.Module):
         self.debug_idx = None             # (idx1, idx2) int32 overrides for parity tests
 
     # ------------------------------------------------------------------ pieces
-    def _style(self, x_rows, z, B, N):
-        """head(cat([x, z])) (Generator.py:163-168) -> [B*N, 128]."""
+    def _style(self, x_rows, z, B, N, activated=True):
+        """head(cat([x, z])) (Generator.py:163-168) -> [B*N, 128].  activated=False returns the values BEFORE the head's
+        last LeakyReLU: the consumers (the two AdaIN style convs) apply it inside their GEMMs."""
         nz = z.shape[-1]
         if self.opts.z_norm:
             z = ops.row_l2_normalize(z if z.is_contiguous() else z.contiguous(), 1e-8)
@@ -179,8 +186,9 @@ class Generator(nn.Module):
         else:
             zz, bcast = z.reshape(B * N, nz), False
         s = ops.ConcatCols.apply(x_rows, zz, N, bcast)
-        s = ops.LRelu.apply(ops.linear(s, self.head[0].weight, self.head[0].bias), NEG)
-        return ops.LRelu.apply(ops.linear(s, self.head[2].weight, self.head[2].bias), NEG)
+        s = ops.linear(s, self.head[0].weight, self.head[0].bias)
+        s = ops.act_linear(s, NEG, self.head[2].weight, self.head[2].bias)      # LeakyReLU(head[0]) inside head[2]'s GEMM
+        return ops.LRelu.apply(s, NEG) if activated else s
 
     def _sphere_graph(self, x, pc_rows, B, N):
         """Neighbour list of EdgeConv1's input.  Without pc_head that input is the sphere itself,
@@ -203,7 +211,7 @@ class Generator(nn.Module):
     def invalidate_sphere_graph(self):
         self._graph_cache = None
 
-    def _body(self, x, x_rows, style, B, N):
+    def _body(self, x, x_rows, style, B, N, style_slope=None):
         pc_rows = x_rows
         if self.use_head:
             slope = self.pc_head[1].negative_slope
@@ -212,14 +220,14 @@ class Generator(nn.Module):
         idx1 = self._sphere_graph(x, pc_rows, B, N)
 
         x1 = self.EdgeConv1.forward_rows(pc_rows, idx1, B, N)
-        x1 = self.adain1.forward_rows(ops.LRelu.apply(x1, NEG_2), style, N)
+        x1 = self.adain1.forward_rows(ops.LRelu.apply(x1, NEG_2), style, N, style_slope)
 
         if self.debug_idx is not None and self.debug_idx[1] is not None:
             idx2 = self.debug_idx[1]
         else:
             idx2 = ops.knn_indices_rows(x1, B, N, self.nk)       # point-major: no [B,C,N] transpose of the features
         x2 = self.EdgeConv2.forward_rows(x1, idx2, B, N)
-        x2 = self.adain2.forward_rows(ops.LRelu.apply(x2, NEG_2), style, N)
+        x2 = self.adain2.forward_rows(ops.LRelu.apply(x2, NEG_2), style, N, style_slope)
         self._last_x1 = x1.detach()
 
         g = ops.SegMax.apply(x2, N)                                              # [B, 128]
@@ -238,8 +246,7 @@ class Generator(nn.Module):
             # tail[0] over cat(global, x2): the global half is constant per cloud -> per-cloud bias
             gb = ops.linear(g, self.tail[0].weight, self.tail[0].bias, cols=(0, ng))           # [B, 256]
             t = ops.AddSegVec.apply(ops.linear(x2, self.tail[0].weight, cols=(ng, W0.shape[1])), gb, N)
-        t = ops.LRelu.apply(t, NEG)
-        t = ops.LRelu.apply(ops.linear(t, self.tail[2].weight, self.tail[2].bias), NEG)
+        t = ops.LRelu.apply(ops.act_linear(t, NEG, self.tail[2].weight, self.tail[2].bias), NEG)   # LeakyReLU(tail[0]) in tail[2]'s GEMM
         o = ops.Tanh.apply(ops.linear(t, self.tail[4].weight, self.tail[4].bias))
         if self.off:
             o = ops.add(pc_rows, o)
@@ -255,8 +262,8 @@ class Generator(nn.Module):
     def forward(self, x, z):
         B, N, _ = x.size()
         x_rows = self._rows(x)
-        style = self._style(x_rows, z, B, N)
-        return self._body(x, x_rows, style, B, N)
+        style = self._style(x_rows, z, B, N, activated=False)
+        return self._body(x, x_rows, style, B, N, style_slope=NEG)
 
     def interpolate(self, x, z1, z2, selection, alpha, use_latent=False):
         """Latent / style blending on the points where selection == 1 (Generator.py:200-261).

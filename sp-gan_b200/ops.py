@@ -905,8 +905,11 @@ def wgrad_bn_act(gz, x_pre, scale, shift, slope, mean, rstd, gamma, beta, W, dir
                              ws_bytes, _stream())
     else:
         a = torch.empty_like(x_pre)                       # recompute the activated input for the weight gradient
-        L().norm_apply(x_pre.data_ptr(), R, K, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                       slope, a.data_ptr(), _stream())
+        if mean is None:                                  # activation-only prologue (ActLinear)
+            L().lrelu(x_pre.data_ptr(), slope, a.data_ptr(), x_pre.numel(), _stream())
+        else:
+            L().norm_apply(x_pre.data_ptr(), R, K, R, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                           slope, a.data_ptr(), _stream())
         gemm_raw(gz, a, None, True, False, out=out, accumulate=direct)
     return None if direct else out.reshape(W.shape)
 
@@ -971,6 +974,90 @@ class BnActLinearTrain(Function):
             if acc is None and params_too:
                 dgamma, dbeta = sgx.view(-1), sg.view(-1)
         return dx, None, None, None, None, dgamma, dbeta, dW, db, None, None, None
+
+
+_UNIT_TABLES = {}
+
+
+def _unit_tables(K, device):
+    """(ones[K], zeros[K]): the identity scale / shift of an activation-only operand prologue."""
+    key = (K, str(device))
+    t = _UNIT_TABLES.get(key)
+    if t is None:
+        t = _UNIT_TABLES[key] = (full((K,), 1.0, device), full((K,), 0.0, device))
+    return t
+
+
+FUSE_ACT_LINEAR = _os.environ.get("SPGAN_FUSE_ACT_LINEAR", "1") != "0"
+
+
+class ActLinear(Function):
+    """z = LeakyReLU_slope(x_pre) @ W^T + b with the activation inside the GEMM's operand converter (spgan_gemm_fused,
+    identity scale / shift): the activated tensor of a conv -> LeakyReLU -> conv pair (Generator.py:107-110,128-133)
+    is never written.  Backward: d x_pre = LeakyReLU'(x_pre) * (g @ W); the weight gradient re-forms the activated
+    operand inside its own converter.  `cols` = (c0, c1) restricts W to an input-channel block.  First order only."""
+
+    @staticmethod
+    def forward(ctx, x_pre, W, bias, slope, cols):
+        x_pre = _c(_rows2d(x_pre))
+        K = x_pre.shape[1]
+        ones, zeros = _unit_tables(K, x_pre.device)
+        res = gemm_fused_raw(x_pre, _wmat(W, cols), bias, tb=True, a_scale=ones, a_shift=zeros, a_slope=slope, wcache=True)
+        if res is None:
+            raise RuntimeError("ActLinear: shape outside spgan_gemm_fused's envelope (caller must check act_linear_ok)")
+        ctx.slope, ctx.cols, ctx.has_bias = slope, cols, bias is not None
+        ctx.save_for_backward(x_pre, W)
+        ctx.set_materialize_grads(False)
+        return res
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        if g is None:
+            return None, None, None, None, None
+        x_pre, W = ctx.saved_tensors
+        g = _c(g)
+        R, K = x_pre.shape
+        Wm = _wmat(W, ctx.cols)
+        dx = dW = db = None
+        params_too = not _INPUT_GRAD_ONLY
+        if ctx.needs_input_grad[1] and params_too:
+            ones, zeros = _unit_tables(K, x_pre.device)
+            direct = _direct_ok(W)
+            if ctx.cols is None:
+                dW = wgrad_bn_act(g, x_pre, ones, zeros, ctx.slope, None, None, None, None, W, direct)
+            else:
+                a = LRelu.apply(x_pre, ctx.slope)
+                if direct:
+                    gemm_raw(g, a, None, True, False, out=_wmat(W.grad, ctx.cols), accumulate=True)
+                else:
+                    blk = gemm_raw(g, a, None, True, False)
+                    dW = full((Wm.shape[0], _wmat(W, None).shape[1]), 0.0, g.device)
+                    dW[:, ctx.cols[0]:ctx.cols[1]] = blk
+                    dW = dW.reshape(W.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2] and params_too:
+            db = ColSum.apply(g, R).view(-1)
+        if ctx.needs_input_grad[0]:
+            ga = gemm_raw(g, Wm, None, False, False, wcache=True)
+            dx = torch.empty_like(ga)
+            L().lrelu_bwd(ga.data_ptr(), x_pre.data_ptr(), ctx.slope, dx.data_ptr(), ga.numel(), _stream())
+        return dx, dW, db, None, None
+
+
+def act_linear_ok(R, weight, cols=None):
+    """Can LeakyReLU(x) @ weight^T run as one spgan_gemm_fused launch (first-order graph, kernel envelope)?"""
+    if not FUSE_ACT_LINEAR or _TWICE_DIFFERENTIABLE or GEMM_ENGINE != 3 or not weight.is_cuda:
+        return False
+    K = _wmat(weight, cols).shape[1]
+    return K % 4 == 0 and L().gemm_fused_workspace(R, weight.shape[0], K, 256, K) != 0
+
+
+def act_linear(x_pre, slope, weight, bias=None, cols=None):
+    """LeakyReLU_slope(x_pre) @ weight^T + bias: fused (ActLinear) where the kernel allows, else the two-op chain."""
+    x2 = _rows2d(x_pre)
+    if act_linear_ok(x2.shape[0], weight, cols) and x2.is_contiguous():
+        return ActLinear.apply(x2, weight, bias, slope, cols)
+    return linear(LRelu.apply(x_pre, slope), weight, bias, cols=cols)
 
 
 def fused_linear_ok(R, weight, bn_in, next_bn=None):

@@ -224,6 +224,36 @@ def test_wgrad_with_operand_prologue_matches_fp64(Mo, No, K):
     assert torch.equal(out2, ops.gemm_raw(gz, x, None, True, False, engine=3))
 
 
+@pytest.mark.parametrize("M,N,K,cols", [(8192, 128, 128, None), (8192, 64, 256, None), (300, 256, 128, None),
+                                        (8192, 256, 128, (64, 192)), (100, 3, 64, None)])
+def test_act_linear_matches_the_two_op_chain(M, N, K, cols):
+    """ops.act_linear: LeakyReLU inside the GEMM's operand converter == LRelu followed by linear, forward and every
+    gradient (the weight gradient re-forms the activated operand in gemm_wg's converter); outside the fused kernel's
+    envelope (N = 3) it IS the two-op chain."""
+    ops = _ops()
+    Kw = K if cols is None else 256
+    x0, W0, b0, r = _rnd(M, K, seed=31), _rnd(N, Kw, 1, seed=32) * 0.1, _rnd(N, seed=33), _rnd(M, N, seed=34)
+    res = []
+    for fused in (True, False):
+        saved = ops.FUSE_ACT_LINEAR
+        ops.FUSE_ACT_LINEAR = fused
+        try:
+            x = x0.cuda().requires_grad_()
+            W = torch.nn.Parameter(W0.cuda())
+            b = torch.nn.Parameter(b0.cuda())
+            out = ops.act_linear(x, 0.01, W, b, cols=cols)
+            ops.MeanScale.apply(ops.Mul.apply(out, r.cuda()), float(r.numel())).backward()
+            res.append((out.detach(), x.grad, W.grad, b.grad))
+        finally:
+            ops.FUSE_ACT_LINEAR = saved
+    ref = torch.nn.functional.leaky_relu(x0.double(), 0.01) @ (W0[:, :, 0] if cols is None else W0[:, cols[0]:cols[1], 0]).double().t() + b0.double()
+    emax, el2 = rel_err(res[0][0].cpu().numpy(), ref.numpy())
+    assert emax < 1e-5 and el2 < 2e-6, (emax, el2)
+    for a, b_, what in zip(res[0], res[1], ("out", "dx", "dW", "db")):
+        emax, el2 = rel_err(a.cpu().numpy(), b_.cpu().numpy())
+        assert emax < 2e-5 and el2 < 1e-5, (what, emax, el2)
+
+
 def test_split_weight_cache_follows_the_parameter():
     """The split (fp16 hi / lo) of a Parameter is kept across products until the parameter changes: in-place updates
     bump its version, raw-pointer updates announce themselves through ops.weights_changed()."""

@@ -34,7 +34,11 @@ def rnd(*shape, seed=0, scale=1.0):
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
 @pytest.mark.parametrize("M,N,K", [(300, 70, 131), (129, 128, 64), (5, 1, 64), (1000, 3, 64), (257, 200, 3),
-                                   (64, 1024, 9000), (128, 1280, 33)])
+                                   (64, 1024, 9000), (128, 1280, 33),
+                                   # the streaming kernels for thin products over many rows (csrc/gemm_skinny.cu)
+                                   (5000, 64, 3), (8192, 3, 64), (4100, 130, 5), (4096, 4, 256), (6000, 2, 8),
+                                   # ... and for the weight gradients of a Conv1d(3, C) (ta: C = A^T B over K rows)
+                                   (64, 3, 20000), (200, 4, 16500), (20, 1, 40000)])
 def test_gemm_all_layouts(ta, tb, M, N, K):
     ops = _ops()
     A = rnd(K, M, seed=1) if ta else rnd(M, K, seed=1)
