@@ -145,7 +145,8 @@ _TN_STATUS = {}               # per-device zeroed status block of the weight-gra
 # Split-weight cache: the tensor engines split every fp32 weight into fp16 hi / lo tiles before the product.  Within
 # one optimiser phase the same weight is multiplied many times (the critic runs five times per step), so the split
 # workspace of a PARAMETER is kept and re-used (transB | 2 in the C ABI) until the weights change: every in-place
-# update bumps the tensor version, FlatAdam (raw-pointer update) calls weights_changed().
+# update bumps the tensor version, FlatAdam (raw-pointer update) calls weights_changed().  Only inside a
+# weight_cache_scope (below).
 _WCACHE = {}
 WEIGHT_EPOCH = 0
 WEIGHT_CACHE = _os.environ.get("SPGAN_WEIGHT_CACHE", "1") != "0"
@@ -155,6 +156,31 @@ def weights_changed():
     global WEIGHT_EPOCH
     WEIGHT_EPOCH += 1
     _WCACHE.clear()
+
+
+_WC_DEPTH = 0
+
+
+class weight_cache_scope:
+    """The split-weight cache is only live inside such a scope, opened by a caller that OWNS the parameter updates
+    (train_step.WGANGPTrainer: every update inside goes through FlatAdam, which calls weights_changed()).  Outside a
+    scope every product splits its weight afresh: a bare module stays correct under any way of writing its weights,
+    including `param.data.copy_()` / raw-pointer writes that bump no version counter.  Entering the outermost scope
+    drops whatever was cached before (the weights may have been touched in between); leaving it drops everything."""
+
+    def __enter__(self):
+        global _WC_DEPTH
+        if _WC_DEPTH == 0:
+            weights_changed()
+        _WC_DEPTH += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _WC_DEPTH
+        _WC_DEPTH -= 1
+        if _WC_DEPTH == 0:
+            _WCACHE.clear()
+        return False
 
 
 def _param_of(t):
@@ -169,7 +195,7 @@ def _cached_ws(kind, Bm, tb, extra, ws_bytes, device):
     """-> (workspace, flag): flag 2 = the workspace already holds the split of this weight.  Entries are tied to the
     Parameter OBJECT (weak reference), not to its address: a freed parameter's address, shape and version can all
     recur in another module."""
-    param = _param_of(Bm)
+    param = _param_of(Bm) if _WC_DEPTH > 0 else None
     if param is None:
         return torch.empty(ws_bytes // 4 + 64, device=device, dtype=torch.float32), 0
     key = (kind, id(param), Bm.data_ptr(), Bm._version, tuple(Bm.shape), tuple(Bm.stride()), bool(tb), extra, WEIGHT_EPOCH)

@@ -85,6 +85,14 @@ class WGANGPTrainer:
         self._graph, self._graph_out, self._static, self.graph_launches = None, None, None, 0
 
     def d_phase(self, x, z, real, alpha=None):
+        with ops.weight_cache_scope():
+            return self._d_phase(x, z, real, alpha)
+
+    def g_phase(self, x, z, real):
+        with ops.weight_cache_scope():
+            return self._g_phase(x, z, real)
+
+    def _d_phase(self, x, z, real, alpha=None):
         G, D = self.G, self.D
         requires_grad(G, False)
         requires_grad(D, True)
@@ -98,7 +106,7 @@ class WGANGPTrainer:
         self.opt_d.step()                   # model.py:260
         return loss_d.detach(), gp.detach()
 
-    def g_phase(self, x, z, real):
+    def _g_phase(self, x, z, real):
         G, D = self.G, self.D
         requires_grad(G, True)
         requires_grad(D, False)
@@ -114,8 +122,9 @@ class WGANGPTrainer:
     def step(self, x, z_d, z_g, real, alpha=None):
         """x [B,N,3] sphere, z_* [B,N,nz], real [B,3,N] (any strides).  Returns device scalars
         (loss_d, gp, loss_g); nothing here synchronises with the host."""
-        loss_d, gp = self.d_phase(x, z_d, real, alpha)
-        loss_g = self.g_phase(x, z_g, real)
+        with ops.weight_cache_scope():         # one scope over both phases: G's weights are split once per step
+            loss_d, gp = self.d_phase(x, z_d, real, alpha)
+            loss_g = self.g_phase(x, z_g, real)
         return loss_d, gp, loss_g
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step

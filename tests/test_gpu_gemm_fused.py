@@ -255,30 +255,38 @@ def test_act_linear_matches_the_two_op_chain(M, N, K, cols):
 
 
 def test_split_weight_cache_follows_the_parameter():
-    """The split (fp16 hi / lo) of a Parameter is kept across products until the parameter changes: in-place updates
-    bump its version, raw-pointer updates announce themselves through ops.weights_changed()."""
+    """Inside a weight_cache_scope (the trainer's) the split (fp16 hi / lo) of a Parameter is kept across products until
+    the parameter changes: in-place updates bump its version, raw-pointer updates announce themselves through
+    ops.weights_changed().  Outside a scope nothing is cached: a bare module stays correct even under writes that bump
+    no version counter (`param.data.copy_()`)."""
     import torch.nn as nn
     ops = _ops()
-    ops.weights_changed()
     W = nn.Parameter(_rnd(96, 128, seed=1).cuda())
     b = nn.Parameter(_rnd(96, seed=2).cuda())
     x = _rnd(4096, 128, seed=3).cuda()
     ref = lambda: (x.double() @ W.detach().double().t() + b.detach().double()).cpu().numpy()
-    y1 = ops.linear(x, W, b)
-    n_entries = len(ops._WCACHE)
-    assert n_entries >= 1
-    y2 = ops.linear(x, W, b)                               # served from the cache
-    assert len(ops._WCACHE) == n_entries and torch.equal(y1, y2)
-    assert rel_err(y2.detach().cpu().numpy(), ref())[1] < 2e-6
-    with torch.no_grad():
-        W.mul_(0.5)                                        # version bump: the old split must not be used
-    y3 = ops.linear(x, W, b)
-    assert rel_err(y3.detach().cpu().numpy(), ref())[1] < 2e-6
-    ops.L().axpby(2.0, W.data_ptr(), 0.0, None, W.data_ptr(), W.numel(), ops._stream())     # raw-pointer update
-    ops.weights_changed()
-    y4 = ops.linear(x, W, b)
-    assert rel_err(y4.detach().cpu().numpy(), ref())[1] < 2e-6
-    # a non-parameter operand is never cached
-    before = len(ops._WCACHE)
-    ops.gemm_raw(x, W.detach().clone(), None, False, True, wcache=True)
-    assert len(ops._WCACHE) == before
+    # ---- outside a scope: never cached, `.data` writes are seen
+    ops.linear(x, W, b)
+    assert len(ops._WCACHE) == 0
+    W.data.copy_(_rnd(96, 128, seed=4).cuda())             # no version bump
+    assert rel_err(ops.linear(x, W, b).detach().cpu().numpy(), ref())[1] < 2e-6
+    with ops.weight_cache_scope():
+        y1 = ops.linear(x, W, b)
+        n_entries = len(ops._WCACHE)
+        assert n_entries >= 1
+        y2 = ops.linear(x, W, b)                               # served from the cache
+        assert len(ops._WCACHE) == n_entries and torch.equal(y1, y2)
+        assert rel_err(y2.detach().cpu().numpy(), ref())[1] < 2e-6
+        with torch.no_grad():
+            W.mul_(0.5)                                        # version bump: the old split must not be used
+        y3 = ops.linear(x, W, b)
+        assert rel_err(y3.detach().cpu().numpy(), ref())[1] < 2e-6
+        ops.L().axpby(2.0, W.data_ptr(), 0.0, None, W.data_ptr(), W.numel(), ops._stream())     # raw-pointer update
+        ops.weights_changed()
+        y4 = ops.linear(x, W, b)
+        assert rel_err(y4.detach().cpu().numpy(), ref())[1] < 2e-6
+        # a non-parameter operand is never cached
+        before = len(ops._WCACHE)
+        ops.gemm_raw(x, W.detach().clone(), None, False, True, wcache=True)
+        assert len(ops._WCACHE) == before
+    assert len(ops._WCACHE) == 0                               # leaving the scope drops everything
