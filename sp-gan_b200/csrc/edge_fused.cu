@@ -205,7 +205,9 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 extern "C" size_t spgan_edge_stats_rows(int64_t P, int C) {
     if (P <= 0 || C < 4 || (C & 3) != 0 || 256 % (C >> 2) != 0) return 0;
-    return (size_t)ew_grid(P * (C >> 2), 256, 16);
+    // 4 CTAs per SM are resident (60 registers): one grid-stride wave.  More CTAs would only mean more partial rows for
+    // the finalize kernel to read (it was 2368 rows = 18 us per BatchNorm; 592 rows = 5 us)
+    return (size_t)ew_grid(P * (C >> 2), 256, 4);
 }
 
 extern "C" int spgan_edge_combine_stats(const float* pc, const float* pn, const int32_t* idx, const float* bias, int64_t P,
@@ -225,7 +227,7 @@ extern "C" int spgan_edge_combine_stats(const float* pc, const float* pn, const 
 
 extern "C" size_t spgan_attn_bwd_rows(int64_t P, int k, int C) {
     if (P <= 0 || k < 1 || k > 16 || C < 1 || C > 256 || 256 % C != 0) return 0;
-    return (size_t)ew_grid(P * C, 256, 32);
+    return (size_t)ew_grid(P * C, 256, 2);          // 2 CTAs per SM are resident (90 registers): one grid-stride wave
 }
 
 extern "C" int spgan_bn_softmax_mul_k_bwd_stats(const float* g, const float* xw, const float* xy, const float* w, int64_t P,
