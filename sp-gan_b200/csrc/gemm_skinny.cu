@@ -79,6 +79,7 @@ gemm_tn_skinny_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, in
 // tiled kernels spend their time on tile bookkeeping (25-40 us where 5-6 us of HBM time are needed).  Exact fp32:
 // one FMA chain over k = 0..K-1 per output, then + bias, then + C.
 constexpr int TK_MAXK = 8, TN_MAXN = 4, TN_MAXK = 256;
+constexpr int TNT_ROWS = 512;                     // rows of K per CTA of the thin weight-gradient kernel
 
 // K <= 8: thread = (row, 4 consecutive columns)
 template <bool VEC>
@@ -162,28 +163,33 @@ gemm_thin_n_kernel(int64_t M, int N, int K, const float* __restrict__ A, int64_t
 template <int MP>                                  // Mo rounded up to 32 / 64 / 128 / 256 (threads per k slice)
 __global__ void __launch_bounds__(256)
 gemm_tn_thin_kernel(int Mo, int No, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
-                    int64_t ldb, float* __restrict__ C, int64_t ldc, int64_t rows_per_cta) {
+                    int64_t ldb, float* __restrict__ C, int64_t ldc) {
     constexpr int SL = 256 / MP;                   // k slices per CTA
+    __shared__ float4 Bs[TNT_ROWS];                // the CTA's rows of X, padded to 4 columns (zero beyond No / K)
     __shared__ float red[SL][MP][4];
     const int m = threadIdx.x % MP, sl = threadIdx.x / MP;
-    const int64_t k0 = (int64_t)blockIdx.x * rows_per_cta;
-    const int64_t k1 = (k0 + rows_per_cta < K) ? k0 + rows_per_cta : K;
+    const int64_t k0 = (int64_t)blockIdx.x * TNT_ROWS;
+    const int rows = (int)((k0 + TNT_ROWS < K ? k0 + TNT_ROWS : K) - k0);
+    for (int i = threadIdx.x; i < TNT_ROWS; i += 256) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < rows)
+            for (int n = 0; n < No; ++n) v[n] = __ldg(B + (k0 + i) * ldb + n);
+        Bs[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const bool live = m < Mo;
-    for (int64_t kb = k0 + sl * 8; kb < k1; kb += SL * 8) {
-        float a[8], b[8][4];
+    const float* ap = A + k0 * lda + m;
+    for (int kb = sl * 8; kb < rows; kb += SL * 8) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = (kb + u < rows && live) ? __ldg(ap + (int64_t)(kb + u) * lda) : 0.f;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int64_t kk = kb + u;
-            const bool ok = kk < k1;
-            a[u] = (ok && live) ? __ldg(A + kk * lda + m) : 0.f;
-#pragma unroll
-            for (int n = 0; n < 4; ++n) b[u][n] = (ok && n < No) ? __ldg(B + kk * ldb + n) : 0.f;
+            const float4 b = Bs[kb + u < TNT_ROWS ? kb + u : TNT_ROWS - 1];       // (a[u] = 0 beyond `rows`)
+            acc[0] = fmaf(a[u], b.x, acc[0]); acc[1] = fmaf(a[u], b.y, acc[1]);
+            acc[2] = fmaf(a[u], b.z, acc[2]); acc[3] = fmaf(a[u], b.w, acc[3]);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-#pragma unroll
-            for (int n = 0; n < 4; ++n) acc[n] = fmaf(a[u], b[u][n], acc[n]);
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n) red[sl][m][n] = acc[n];
@@ -232,15 +238,11 @@ int spgan_gemm_tn_skinny(int64_t Mo, int No, int64_t K, const float* A, int64_t 
         if (e != cudaSuccess) return (int)e;
     }
     if (No <= 4 && Mo <= 256) {
-        int64_t ctas = 4 * kNumSMs;
-        int64_t rows = ceil_div64(ceil_div64(K, ctas), 64) * 64;
-        if (rows < 256) rows = 256;
-        ctas = ceil_div64(K, rows);
-        const unsigned g = (unsigned)ctas;
-        if (Mo <= 32) gemm_tn_thin_kernel<32><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc, rows);
-        else if (Mo <= 64) gemm_tn_thin_kernel<64><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc, rows);
-        else if (Mo <= 128) gemm_tn_thin_kernel<128><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc, rows);
-        else gemm_tn_thin_kernel<256><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc, rows);
+        const unsigned g = (unsigned)ceil_div64(K, TNT_ROWS);
+        if (Mo <= 32) gemm_tn_thin_kernel<32><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc);
+        else if (Mo <= 64) gemm_tn_thin_kernel<64><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc);
+        else if (Mo <= 128) gemm_tn_thin_kernel<128><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc);
+        else gemm_tn_thin_kernel<256><<<g, 256, 0, st>>>((int)Mo, No, K, A, lda, B, ldb, C, ldc);
         return spgan_launch_status();
     }
     int64_t ctas = 2 * kNumSMs;
