@@ -174,6 +174,10 @@ int spgan_split_cols_add(const float *g, int64_t R, int Ca, int Cb, float *ga, f
  * The first int of the workspace is a status word: non-zero after completion means the kernel
  * aborted on an internal pipeline timeout (never expected; checked by the tests). */
 size_t spgan_gemm_workspace(int engine, int N, int K);
+/* 1 when spgan_gemm (engine 3, transA = 0) runs this product on the chunked-K kernel of csrc/gemm_ts.cu (K > 256,
+ * K % 128 == 0, 16-byte aligned A): the layout of the split weight kept in the workspace differs between the kernels,
+ * so a caller that re-uses a workspace (transB | 2) must key it on this. */
+size_t spgan_gemm_bigk_route(int64_t M, int N, int K, const float *A, int64_t lda);
 /* Workspace of the weight-gradient form (transA = 1, transB = 0: C[Mo,No] = A^T B, K = rows) on engine 3: a 256-byte
  * status block plus the split-K partial tiles [k_chunks, Mo, No] that csrc/gemm_wg.cu adds up in a fixed order
  * (deterministic; the engine-1 kernel, taken for shapes / alignments outside gemm_wg.cu's envelope or when the

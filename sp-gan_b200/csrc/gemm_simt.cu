@@ -295,6 +295,7 @@ bool spgan_gemm_ts_supported(int64_t M, int N, int K, const float* A, int64_t ld
 int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                   int64_t ldc, const float* bias, int accumulate, const float* a_scale, const float* a_shift, float a_slope,
                   float* col_sum, float* col_sqsum, void* workspace, cudaStream_t st);
+bool spgan_gemm_tsk_supported(int64_t M, int N, int K, const float* A, int64_t lda);
 bool spgan_gemm_wg_supported(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb);
 size_t spgan_gemm_wg_workspace(int64_t Mo, int No, int64_t K);
 int spgan_gemm_wg(int64_t Mo, int No, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
@@ -325,8 +326,15 @@ extern "C" size_t spgan_gemm_workspace(int engine, int N, int K) {
     if (N < 1 || K < 1) return 0;
     // deterministic split-K partial tiles of the small-batch path (any engine)
     const size_t small_m = (K >= 256 && K < 2048) ? (size_t)kSmallMSplits * kSmallMRows * N * sizeof(float) : 0;
-    const size_t tc = (engine >= 1 && engine <= 3) ? spgan_gemm_tc_workspace(N, K) : 0;
+    size_t tc = (engine >= 1 && engine <= 3) ? spgan_gemm_tc_workspace(N, K) : 0;
+    if (engine == 3) { const size_t ts = spgan_gemm_ts_workspace(N, K); if (ts > tc) tc = ts; }
     return small_m > tc ? small_m : tc;
+}
+
+/* 1 when spgan_gemm(engine 3, no transA) sends this product to the chunked-K TMEM-resident kernel (gemm_ts.cu): the
+ * layout of the split weight in the workspace depends on the route, so a caller that caches workspaces keys on it */
+extern "C" size_t spgan_gemm_bigk_route(int64_t M, int N, int K, const float* A, int64_t lda) {
+    return (ts_enabled() && spgan_gemm_tsk_supported(M, N, K, A, lda)) ? 1 : 0;
 }
 
 extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda,
@@ -339,6 +347,11 @@ extern "C" int spgan_gemm(int transA, int transB, int64_t M, int N, int K, const
     if (M == 0) return SPGAN_OK;
     // engine 3, K <= 256: the TMEM-resident-A kernel (gemm_ts.cu); SPGAN_TS=0 routes these to gemm_tc.cu instead
     if (engine == 3 && !transA && workspace != nullptr && ts_enabled() && spgan_gemm_ts_supported(M, N, K, A, lda) &&
+        workspace_bytes >= spgan_gemm_ts_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
+        return spgan_gemm_ts(transB | presplit, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, nullptr, 1.f, nullptr,
+                             nullptr, workspace, as_stream(stream));
+    // engine 3, K > 256, K % 128 == 0: the same kernel family with K walked in chunks (gemm_tsk_kernel)
+    if (engine == 3 && !transA && workspace != nullptr && ts_enabled() && spgan_gemm_tsk_supported(M, N, K, A, lda) &&
         workspace_bytes >= spgan_gemm_ts_workspace(N, K) && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0)
         return spgan_gemm_ts(transB | presplit, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, nullptr, nullptr, 1.f, nullptr,
                              nullptr, workspace, as_stream(stream));

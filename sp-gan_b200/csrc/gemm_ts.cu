@@ -455,6 +455,275 @@ gemm_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// =================================================================================================================
+// K > 256 (the critic's fc2 input gradient, K = 1024; EdgeBlock's conv_out, K = k * F = 1280; Generator.py:71,
+// Discriminator.py:64 under autograd): the same machinery with K walked in CHUNKS of 128 (two k-blocks).
+//   * TMEM: [0,256) the accumulators of TWO column tiles (a column GROUP, 128 output columns), resident over the whole K
+//     loop; [256,512) two A regions of one chunk each: the conversion of chunk c+1 overlaps the MMAs of chunk c.
+//   * loop order (every role): row tile -> column group -> K chunk -> column tile of the group -> k-block.  A is
+//     re-staged and re-converted once per column group (L2-resident: the CTA finished reading it moments ago).
+//   * the epilogue drains a group's two tiles after its last chunk; the next group's first MMAs wait per tile for that.
+// No prologue / statistics here (no K > 256 layer is followed or preceded by a BatchNorm that needs them).  K % 128 == 0.
+__global__ void __launch_bounds__(TS_THREADS, 1)
+gemm_tsk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TsParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = tc::align_smem_1024(smem_raw);
+    unsigned char* smA = smem;
+    unsigned char* smB = smA + A_STAGES * A_STAGE_BYTES;
+    float* epi_smem = reinterpret_cast<float*>(smB + B_STAGES * B_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(epi_smem) + EPI_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar = [&](int slot) { return bar0 + 8u * slot; };
+    volatile int* vstatus = p.status;
+
+    const int NCH = p.K / (2 * BK);                        // chunks of two k-blocks
+    const int m_tiles = (int)((p.M + BM - 1) / BM);
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int n_groups = (n_tiles + 1) / 2;
+
+    if (tid == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(bar(BAR_SA_FULL + s), 1); mbar_init(bar(BAR_SA_EMPTY + s), 8); }
+        for (int s = 0; s < 4; ++s) mbar_init(bar(BAR_TA_FULL + s), 8);
+        for (int s = 0; s < 2; ++s) mbar_init(bar(BAR_TA_EMPTY + s), 1);
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bar(BAR_SB_FULL + s), 1); mbar_init(bar(BAR_SB_EMPTY + s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar(BAR_D_FULL + s), 1); mbar_init(bar(BAR_D_EMPTY + s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == TMA_A_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    if (warp == TMA_B_WARP && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) __trap();                          // see gemm_ts_kernel
+
+    if (warp == TMA_A_WARP) {
+        // ================================================================ TMA producer: fp32 A k-blocks, chunk by chunk
+        const uint32_t sA0 = smem_u32(smA);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+            for (int ng = 0; ng < n_groups; ++ng)
+                for (int kb = 0; kb < 2 * NCH; ++kb) {
+                    mbar_wait(bar(BAR_SA_EMPTY + stage), phase ^ 1, vstatus);
+                    if (elect_one()) {
+                        const uint32_t dst = sA0 + (uint32_t)(stage * A_STAGE_BYTES);
+                        mbar_expect_tx(bar(BAR_SA_FULL + stage), A_STAGE_BYTES);
+                        tma_load_2d(dst, &tmA, kb * BK, mt * BM, bar(BAR_SA_FULL + stage));
+                        tma_load_2d(dst + BM * 128, &tmA, kb * BK + 32, mt * BM, bar(BAR_SA_FULL + stage));
+                    }
+                    __syncwarp();
+                    if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+                }
+    } else if (warp == TMA_B_WARP) {
+        // ================================================================ TMA producer: [W_hi ; W_lo] tiles
+        const uint32_t sB0 = smem_u32(smB);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+            for (int ng = 0; ng < n_groups; ++ng) {
+                const int gt = min(2, n_tiles - 2 * ng);
+                for (int ch = 0; ch < NCH; ++ch)
+                    for (int t = 0; t < gt; ++t)
+                        for (int kb = 0; kb < 2; ++kb) {
+                            mbar_wait(bar(BAR_SB_EMPTY + stage), phase ^ 1, vstatus);
+                            if (elect_one()) {
+                                mbar_expect_tx(bar(BAR_SB_FULL + stage), B_STAGE_BYTES);
+                                tma_load_2d(sB0 + (uint32_t)(stage * B_STAGE_BYTES), &tmB, (2 * ch + kb) * BK,
+                                            (2 * ng + t) * 2 * BN, bar(BAR_SB_FULL + stage));
+                            }
+                            __syncwarp();
+                            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+                        }
+            }
+    } else if (warp == MMA_WARP) {
+        // ================================================================ MMA issuer
+        constexpr uint32_t idesc_main = make_idesc_f16(BM, 2 * BN);
+        constexpr uint32_t idesc_x = make_idesc_f16(BM, BN);
+        const uint32_t sB0 = smem_u32(smB);
+        int sb = 0;
+        uint32_t sb_phase = 0, ta_par0 = 0, ta_par1 = 0, d_par0 = 0, d_par1 = 0;
+        int vt = 0;                                        // running chunk count: A region = vt & 1
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+            for (int ng = 0; ng < n_groups; ++ng) {
+                const int gt = min(2, n_tiles - 2 * ng);
+                for (int ch = 0; ch < NCH; ++ch, ++vt) {
+                    const int g = vt & 1;
+                    const uint32_t a_base = TMEM_A0 + (uint32_t)(g * 128);
+                    const uint32_t ta_par = g ? ta_par1 : ta_par0;
+                    for (int t = 0; t < gt; ++t) {
+                        if (ch == 0) {                     // the tile's accumulator must have been drained (previous group)
+                            mbar_wait(bar(BAR_D_EMPTY + t), (t ? d_par1 : d_par0) ^ 1, vstatus);
+                            tc_fence_after();
+                        }
+                        const uint32_t d_main = (uint32_t)(t * 2 * BN);
+                        const uint32_t d_x = d_main + BN;
+                        for (int kb = 0; kb < 2; ++kb) {
+                            if (t == 0) mbar_wait(bar(BAR_TA_FULL + g * 2 + kb), ta_par, vstatus);
+                            mbar_wait(bar(BAR_SB_FULL + sb), sb_phase, vstatus);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t bd = make_desc_sw128(sB0 + (uint32_t)(sb * B_STAGE_BYTES));
+#pragma unroll
+                                for (int s = 0; s < 4; ++s) {
+                                    const uint32_t a_hi = a_base + (uint32_t)(kb * 64 + s * 8);
+                                    umma_ts(d_main, a_hi, bd + (uint64_t)(s * 2), idesc_main, (ch > 0 || kb > 0 || s > 0) ? 1u : 0u);
+                                    umma_ts(d_x, a_hi + 32, bd + (uint64_t)(s * 2), idesc_x, 1u);
+                                }
+                                umma_commit(bar(BAR_SB_EMPTY + sb));
+                            }
+                            __syncwarp();
+                            if (++sb == B_STAGES) { sb = 0; sb_phase ^= 1; }
+                        }
+                        if (ch == NCH - 1) {               // the tile is complete
+                            if (elect_one()) umma_commit(bar(BAR_D_FULL + t));
+                            __syncwarp();
+                            if (t) d_par1 ^= 1; else d_par0 ^= 1;
+                        }
+                    }
+                    if (elect_one()) umma_commit(bar(BAR_TA_EMPTY + g));       // the chunk's A region may be overwritten
+                    __syncwarp();
+                    if (g) ta_par1 ^= 1; else ta_par0 ^= 1;
+                }
+            }
+    } else if (warp < EPI_WARP0) {
+        // ================================================================ converters: staged fp32 -> hi/lo -> TMEM
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        int stage = 0;
+        uint32_t sa_phase = 0, te_par0 = 0, te_par1 = 0;
+        int vt = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+            for (int ng = 0; ng < n_groups; ++ng)
+                for (int ch = 0; ch < NCH; ++ch, ++vt) {
+                    const int g = vt & 1;
+                    if (vt >= 2) {                         // the region's previous chunk must have been consumed
+                        mbar_wait(bar(BAR_TA_EMPTY + g), g ? te_par1 : te_par0, vstatus);
+                        if (g) te_par1 ^= 1; else te_par0 ^= 1;
+                        tc_fence_after();
+                    }
+                    const uint32_t a_base = tmem_base + TMEM_A0 + (uint32_t)(g * 128) + lane_addr;
+                    for (int kb = 0; kb < 2; ++kb) {
+                        mbar_wait(bar(BAR_SA_FULL + stage), sa_phase, vstatus);
+                        const unsigned char* box = smA + stage * A_STAGE_BYTES + h * (BM * 128) + row * 128;
+                        float v[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(box + ((c ^ (row & 7)) << 4));
+                            v[4 * c] = t4.x; v[4 * c + 1] = t4.y; v[4 * c + 2] = t4.z; v[4 * c + 3] = t4.w;
+                        }
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+                            float h0, h1;
+                            asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+                                : "=f"(h0), "=f"(h1) : "r"(hi[i]));
+                            const float r0 = (v[2 * i] - h0) * 2048.f, r1 = (v[2 * i + 1] - h1) * 2048.f;
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo[i]) : "f"(r1), "f"(r0));
+                        }
+                        warp_arrive(bar(BAR_SA_EMPTY + stage), lane);
+                        tmem_st16(a_base + (uint32_t)(kb * 64 + h * 16), hi);
+                        tmem_st16(a_base + (uint32_t)(kb * 64 + 32 + h * 16), lo);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        warp_arrive(bar(BAR_TA_FULL + g * 2 + kb), lane);
+                        if (++stage == A_STAGES) { stage = 0; sa_phase ^= 1; }
+                    }
+                }
+    } else {
+        // ================================================================ epilogue (warps 8..15)
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, h = ew >> 2;
+        float* T = epi_smem + ew * (32 * 32);
+        uint32_t d_par0 = 0, d_par1 = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+            const int64_t m0 = (int64_t)mt * BM + q * 32;
+            for (int ng = 0; ng < n_groups; ++ng) {
+                const int gt = min(2, n_tiles - 2 * ng);
+                for (int t = 0; t < gt; ++t) {
+                    const int n0 = (2 * ng + t) * BN + h * 32;
+                    const int colv = n0 + (lane & 7) * 4;
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool col_ok = p.vecC && colv + 4 <= p.N;
+                    if (p.bias != nullptr && col_ok) bb = __ldg(reinterpret_cast<const float4*>(p.bias + colv));
+                    mbar_wait(bar(BAR_D_FULL + t), t ? d_par1 : d_par0, vstatus);
+                    if (t) d_par1 ^= 1; else d_par0 ^= 1;
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 2 * BN + h * 32);
+                    float v[32];
+                    {
+                        uint32_t rv[32], rw[32];
+                        tmem_ld32_issue(taddr, rv);
+                        tmem_ld32_issue(taddr + BN, rw);
+                        tmem_ld_wait();
+                        tmem_pin32(rv);
+                        tmem_pin32(rw);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rw[j]), 1.f / 2048.f, __uint_as_float(rv[j]));
+                    }
+                    tc_fence_before();
+                    warp_arrive(bar(BAR_D_EMPTY + t), lane);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(T + lane * 32 + 4 * (c ^ (lane & 7))) =
+                            make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    __syncwarp();
+                    const int g8 = lane & 7;
+                    if (col_ok && m0 + 32 <= p.M) {
+                        float* cp = p.C + (m0 + (lane >> 3)) * p.ldc + colv;
+                        const int64_t step = 4 * p.ldc;
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const int r = rr * 4 + (lane >> 3);
+                            float4 o = *reinterpret_cast<const float4*>(T + r * 32 + 4 * (g8 ^ (r & 7)));
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            if (p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(cp);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *reinterpret_cast<float4*>(cp) = o;
+                            cp += step;
+                        }
+                    } else if (n0 < p.N) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const int r = rr * 4 + (lane >> 3);
+                            const int64_t grow = m0 + r;
+                            if (grow >= p.M) continue;
+                            const float4 t4 = *reinterpret_cast<const float4*>(T + r * 32 + 4 * (g8 ^ (r & 7)));
+                            const float ov[4] = {t4.x, t4.y, t4.z, t4.w};
+                            float* cp = p.C + grow * p.ldc + colv;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (colv + j >= p.N) continue;
+                                float o = ov[j];
+                                if (p.bias != nullptr) o += __ldg(p.bias + colv + j);
+                                if (p.accumulate) o += cp[j];
+                                cp[j] = o;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // W (weights) -> zero-padded fp16 hi / 2^11-scaled lo, laid out per 64-row column tile as [hi rows ; lo rows] x Kp
 // (one TMA box = one [W_hi ; W_lo] operand tile); clears the status word
 __global__ void presplit_w_kernel(const float* __restrict__ B, int64_t ldb, int transB, int N, int K, int n_tiles, int Kp,
@@ -505,6 +774,15 @@ bool spgan_gemm_ts_supported(int64_t M, int N, int K, const float* A, int64_t ld
            (reinterpret_cast<uintptr_t>(A) & 15) == 0 && encode_tiled_fn() != nullptr;
 }
 
+// K > 256 through gemm_tsk_kernel (plain product: no prologue, no statistics); SPGAN_TSK=0 leaves these to gemm_tc.cu.
+// K <= 1536: one accumulation chain per output in the truncating fp32 TMEM accumulator (~1.2e-9 relative per k:
+// 1.5e-6 rms at K = 1280, the step's largest; longer K stays with gemm_tc.cu).
+bool spgan_gemm_tsk_supported(int64_t M, int N, int K, const float* A, int64_t lda) {
+    static const bool on = [] { const char* e = getenv("SPGAN_TSK"); return !(e && e[0] == '0'); }();
+    return on && M >= BM && M < (1LL << 31) && N >= 16 && K > MAX_KB * BK && K <= 1536 && K % (2 * BK) == 0 && (lda % 4) == 0 &&
+           (reinterpret_cast<uintptr_t>(A) & 15) == 0 && encode_tiled_fn() != nullptr;
+}
+
 int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                   int64_t ldc, const float* bias, int accumulate, const float* a_scale, const float* a_shift, float a_slope,
                   float* col_sum, float* col_sqsum, void* workspace, cudaStream_t st) {
@@ -549,10 +827,17 @@ int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t l
     p.col_sum = col_sum; p.col_sqsum = col_sqsum; p.status = status;
     p.vecC = ((ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
               (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
-    cudaError_t e = cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
     const int m_tiles = (int)((M + BM - 1) / BM);
     const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
+    if (K > MAX_KB * BK) {
+        if (a_scale != nullptr || col_sum != nullptr || K % (2 * BK) != 0) return SPGAN_E_UNSUPPORTED;
+        cudaError_t e = cudaFuncSetAttribute(gemm_tsk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        gemm_tsk_kernel<<<grid, TS_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+        return spgan_launch_status();
+    }
+    cudaError_t e = cudaFuncSetAttribute(gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
     gemm_ts_kernel<<<grid, TS_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
     return spgan_launch_status();
 }

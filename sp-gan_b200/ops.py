@@ -244,7 +244,8 @@ def gemm_raw(A, B, bias=None, ta=False, tb=False, out=None, accumulate=False, en
         ws_bytes = L().gemm_workspace(engine, N, K)
         if tc and wcache and WEIGHT_CACHE:
             # the route (gemm_ts vs gemm_tc) is part of the key: it fixes the layout of the split
-            route = engine == 3 and L().gemm_fused_workspace(M, N, K, A.data_ptr(), lda) != 0
+            route = (engine == 3 and L().gemm_fused_workspace(M, N, K, A.data_ptr(), lda) != 0,
+                     engine == 3 and not ta and L().gemm_bigk_route(M, N, K, A.data_ptr(), lda) != 0)
             ws, wflag = _cached_ws("gemm", B, tb, (engine, route), ws_bytes, A.device)
         else:
             ws = torch.empty(ws_bytes // 4 + 64, device=A.device, dtype=torch.float32)

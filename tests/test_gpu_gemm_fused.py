@@ -99,6 +99,34 @@ def test_fused_pipeline_under_repetition_on_the_step_shapes(M, N, K):
     assert torch.equal(first, out), "same operands, same result bit for bit"
 
 
+@pytest.mark.parametrize("tb", [True, False])
+@pytest.mark.parametrize("M,N,K", [(131072, 256, 1024), (4096, 128, 1280), (1000, 72, 512), (300, 64, 384), (5000, 192, 640),
+                                   (129, 1280, 512), (2048, 16, 1536)])
+def test_chunked_k_kernel_matches_fp64(M, N, K, tb):
+    """K > 256 on engine 3: gemm_tsk_kernel (K walked in chunks of 128 with the accumulators of a column group resident
+    in TMEM): fp64 parity incl. bias, C +=, odd column-tile counts and ragged edges; bit-identical repeats."""
+    ops = _ops()
+    A = _rnd(M, K, seed=41).cuda()
+    B = (_rnd(N, K, seed=42) if tb else _rnd(K, N, seed=42)).cuda()
+    bias = _rnd(N, seed=43).cuda()
+    assert ops.L().gemm_bigk_route(M, N, K, A.data_ptr(), K) == 1
+    ref = A.double().cpu() @ (B.t() if tb else B).double().cpu() + bias.double().cpu()
+    out = ops.gemm_raw(A, B, bias, False, tb, engine=3)
+    assert _status(ops) == 0
+    # the tensor core adds into the fp32 TMEM accumulator with truncation: ~1.2e-9 relative per k of the chain
+    tol2 = 2e-6 * max(1.0, K / 1024.0)
+    emax, el2 = rel_err(out.cpu().numpy(), ref.numpy())
+    assert emax < 1e-5 and el2 < tol2, (emax, el2)
+    out2 = ops.gemm_raw(A, B, bias, False, tb, engine=3)
+    assert torch.equal(out, out2)
+    ops.gemm_raw(A, B, None, False, tb, out=out2, accumulate=True, engine=3)
+    emax, el2 = rel_err(out2.cpu().numpy(), (2 * ref - bias.double().cpu()).numpy())
+    assert emax < 1e-5 and el2 < tol2, (emax, el2)
+    for _ in range(30):                                   # the pipeline back to back
+        ops.gemm_raw(A, B, bias, False, tb, out=out2, engine=3)
+    assert _status(ops) == 0 and torch.equal(out, out2)
+
+
 def test_fused_strided_operands_and_unsupported_shapes():
     ops = _ops()
     big = _rnd(5000, 256, seed=9).cuda()
