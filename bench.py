@@ -285,12 +285,32 @@ def run_gpu(args, real_stdout):
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     losses = []
 
+    # The three step results go device -> pinned host right behind the step, on the same stream (the graph's output
+    # scalars are overwritten by the next replay); the host READS step i's numbers while step i+1 runs, so the
+    # read-back costs the GPU no idle time.  Every step's inputs are copied and every step's results are read inside
+    # the timed region; the last step's are awaited before it closes.
+    loss_host = torch.empty((args.steps, 3), dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event() for _ in range(args.steps)]
+
+    def read_back(i):
+        loss_ev[i].synchronize()
+        losses.append(loss_host[i].tolist())
+
     def e2e_step(i):
         if use_graph:                           # pinned host -> the graph's static input buffers
             out = step_on(host[i % n_pool])
         else:
             out = step_on({k: v.to(dev, non_blocking=True) for k, v in host[i % n_pool].items()})
-        losses.append([float(t) for t in out])                              # D2H of the three step results
+        if os.environ.get("SPGAN_BENCH_SYNC_READ") == "1":                    # A/B: blocking read-back every step
+            losses.append([float(t) for t in out])
+            return
+        for j, t in enumerate(out):                                          # D2H of the three step results
+            loss_host[i, j].copy_(t, non_blocking=True)
+        loss_ev[i].record()
+        if i > 0:
+            read_back(i - 1)
+        if i == args.steps - 1:
+            read_back(i)
 
     ms_e2e = timed(e2e_step, args.steps) if not minimal else float("nan")
     e2e = {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,

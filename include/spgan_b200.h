@@ -293,6 +293,12 @@ int spgan_norm_bwd_reduce(const float *g, const float *x, float slope, int64_t R
 int spgan_norm_bwd_apply(const float *g, const float *x, float slope, int64_t R, int C, int64_t seg_rows,
                          const float *mean, const float *rstd, const float *gamma, const float *beta,
                          const float *sg, const float *sgx, float *dx, spgan_stream_t stream);
+/* spgan_norm_bwd_apply (one segment) with dx = (the BatchNorm backward) + addend[R, C]: under the gradient penalty's
+ * final backward pass the input of a BatchNorm receives a second gradient term from the double-backward node
+ * (gradient_penalty.py:31-37); adding it here replaces autograd's separate accumulation pass.  C % 4 == 0. */
+int spgan_norm_bwd_apply_add(const float *g, const float *x, float slope, int64_t R, int C, const float *mean,
+                             const float *rstd, const float *gamma, const float *beta, const float *sg,
+                             const float *sgx, const float *addend, float *dx, spgan_stream_t stream);
 /* Second-order (double) backward of train-mode batch norm, needed by the gradient penalty
  * (gradient_penalty.py:31-33 with create_graph=True).  Inputs: first-backward operands
  * (g = dL/dy, x, gamma, mean, rstd) and u = d(loss)/d(dx).  Outputs: gg = d/dg, gx = d/dx,

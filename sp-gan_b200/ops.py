@@ -670,7 +670,7 @@ def _direct_ok(*params):
     return True
 
 
-def _norm_bwd(g, x, slope, seg_rows, mean, rstd, gamma, beta, acc=None):
+def _norm_bwd(g, x, slope, seg_rows, mean, rstd, gamma, beta, acc=None, addend=None):
     """(dx, sum g', sum g' xhat) of y = LeakyReLU_slope(norm(x) * gamma + beta); the activation mask is
     recomputed from x inside the kernels (slope 1 = no activation).  acc = (gamma_param, beta_param): their .grad
     receive dgamma / dbeta in place from the reduction's finalize pass (one segment only)."""
@@ -689,17 +689,25 @@ def _norm_bwd(g, x, slope, seg_rows, mean, rstd, gamma, beta, acc=None):
         L().norm_bwd_reduce(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
                             sg.data_ptr(), sgx.data_ptr(), ws.data_ptr(), _stream())
     dx = torch.empty_like(x)
+    if addend is not None and seg_rows == R and C % 4 == 0 and addend.is_contiguous():
+        # dx = BatchNorm backward + a second gradient term of x handed over by the double-backward node
+        L().norm_bwd_apply_add(g.data_ptr(), x.data_ptr(), slope, R, C, mean.data_ptr(), rstd.data_ptr(), gp, bp,
+                               sg.data_ptr(), sgx.data_ptr(), addend.data_ptr(), dx.data_ptr(), _stream())
+        return dx, sg, sgx
     L().norm_bwd_apply(g.data_ptr(), x.data_ptr(), slope, R, C, seg_rows, mean.data_ptr(), rstd.data_ptr(), gp, bp,
                        sg.data_ptr(), sgx.data_ptr(), dx.data_ptr(), _stream())
+    if addend is not None:
+        dx = add(dx, addend)
     return dx, sg, sgx
 
 
-def _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, slope):
+def _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, slope, addend=None):
     """Shared first-order backward of the train-mode BatchNorm Functions when no higher-order graph is being built:
-    dgamma / dbeta go straight into the parameters' .grad where possible."""
+    dgamma / dbeta go straight into the parameters' .grad where possible.  addend: a second gradient term of x (from
+    the double-backward node of the same layer), added inside the apply kernel."""
     acc = (gamma, beta) if (ctx.needs_input_grad[1] and ctx.needs_input_grad[2] and not _INPUT_GRAD_ONLY
                             and _direct_ok(gamma, beta)) else None
-    dx, sg, sgx = _norm_bwd(_c(gy), x, slope, x.shape[0], mean, rstd, gamma, beta, acc)
+    dx, sg, sgx = _norm_bwd(_c(gy), x, slope, x.shape[0], mean, rstd, gamma, beta, acc, addend)
     if acc is not None or _INPUT_GRAD_ONLY:
         return dx, None, None
     return dx, sgx.view(-1), sg.view(-1)
@@ -792,11 +800,19 @@ class BatchNormActTrain2(Function):
     @staticmethod
     def backward(ctx, gy, _gm, _gv):
         x, gamma, beta, mean, rstd = ctx.saved_tensors
+        link = getattr(ctx, "link", None)
+        if not torch.is_grad_enabled():            # the final (first-order) pass over the penalty's graph
+            # The double-backward node of this layer ran earlier in this pass (it was created later) and left ITS
+            # gradient term for x here instead of returning it: the two terms are summed inside the apply kernel, not
+            # by a separate accumulation pass of autograd over the [P, C] tensor.
+            extra = link.pop("gx", None) if link else None
+            if gy is None:
+                return extra, None, None, None, None, None
+            return _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, ctx.slope, extra) + (None, None, None)
         if gy is None:
             return None, None, None, None, None, None
-        if not torch.is_grad_enabled():            # the final (first-order) pass over the penalty's graph
-            return _bn_bwd_direct(ctx, gy, x, gamma, beta, mean, rstd, ctx.slope) + (None, None, None)
-        dx, dgamma, dbeta = BatchNormActTrainBwd2.apply(gy, x, gamma, beta, mean, rstd, ctx.slope)
+        link = ctx.link = {"fwd": weakref.ref(ctx)}      # (weak: ctx -> link -> ctx would keep the saved activations alive)
+        dx, dgamma, dbeta = BatchNormActTrainBwd2.apply(gy, x, gamma, beta, mean, rstd, ctx.slope, link)
         if _INPUT_GRAD_ONLY:
             dgamma = dbeta = None
         return dx, dgamma, dbeta, None, None, None
@@ -807,11 +823,12 @@ class BatchNormActTrainBwd2(Function):
     cotangent on dx (the mask is piecewise constant in x: it multiplies g on the way in and gg on the way out)."""
 
     @staticmethod
-    def forward(ctx, g, x, gamma, beta, mean, rstd, slope):
+    def forward(ctx, g, x, gamma, beta, mean, rstd, slope, link=None):
         g = _c(g)
         ctx.set_materialize_grads(False)
         dx, sg, sgx = _norm_bwd(g, x, slope, x.shape[0], mean, rstd, gamma, beta)
-        ctx.slope = slope
+        ctx.slope, ctx.link = slope, link
+        ctx.hand_over = link is not None and ctx.needs_input_grad[1]
         ctx.save_for_backward(g, x, gamma, beta, mean, rstd)
         return dx, sgx.view(-1), sg.view(-1)
 
@@ -823,7 +840,7 @@ class BatchNormActTrainBwd2(Function):
             raise NotImplementedError("double backward through BatchNorm parameter gradients is not needed by "
                                       "the WGAN-GP step (only_inputs=True) and is not implemented")
         if u is None:
-            return None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         u = _c(u)
         R, C = x.shape
         sums = torch.empty((5, C), device=x.device, dtype=torch.float32)
@@ -836,7 +853,25 @@ class BatchNormActTrainBwd2(Function):
         L().bn_act_dbl_bwd_apply(g.data_ptr(), u.data_ptr(), x.data_ptr(), ctx.slope, R, C, mean.data_ptr(),
                                  rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), sums.data_ptr(), gg.data_ptr(),
                                  gx.data_ptr(), ggamma.data_ptr(), _stream())
-        return gg, gx, ggamma, None, None, None, None
+        fwd = ctx.link["fwd"]() if ctx.hand_over else None
+        if fwd is not None and FUSE_GP_ACCUMULATE and _node_will_run(fwd):
+            ctx.link["gx"] = gx                    # picked up by BatchNormActTrain2.backward of the same layer (see there)
+            gx = None
+        return gg, gx, ggamma, None, None, None, None, None
+
+
+FUSE_GP_ACCUMULATE = _os.environ.get("SPGAN_FUSE_GP_ACCUMULATE", "1") != "0"
+
+
+def _node_will_run(node):
+    """Will the autograd engine execute `node` in the backward pass that is running now?  (The hand-over of a gradient
+    term to a node is only sound if that node's backward really follows; otherwise the term is returned the normal way.)"""
+    if node is None:
+        return False
+    try:
+        return bool(torch._C._will_engine_execute_node(node))
+    except Exception:                                        # noqa: BLE001 -- private API: absent or refusing = no hand-over
+        return False
 
 
 class BatchNormActTrain(Function):

@@ -558,3 +558,32 @@ def test_bn_act_softmax_mul_k_fused_equals_unfused_chain(P, k, C):
     close(res[0]["out"], ref.float(), 1e-5, "out vs torch")
     close(res[0]["dxw"], a.grad.float(), 1e-4, "dxw vs torch")
     close(res[0]["dxy"], b.grad.float(), 1e-4, "dxy vs torch")
+
+
+def test_gradient_penalty_accumulation_handed_to_the_bn_backward():
+    """Under the penalty's final backward the input of every BatchNorm gets two gradient terms (the layer's own backward
+    and its double-backward node).  With the hand-over the second term is added inside the BatchNorm backward's apply
+    kernel instead of by autograd's accumulation pass: same gradients, fewer kernels."""
+    import spgan_b200 as pkg
+    from oracle import spgan_ref as R
+    ops = _ops()
+    o = R.default_opts(np=256)
+    real, fake = rnd(3, 3, 256, seed=70) * 0.5, rnd(3, 3, 256, seed=71) * 0.5
+    alpha = torch.rand(3, 1, 1, generator=torch.Generator().manual_seed(5))
+    res = {}
+    for on in (True, False):
+        saved = ops.FUSE_GP_ACCUMULATE
+        ops.FUSE_GP_ACCUMULATE = on
+        try:
+            D = pkg.Discriminator(o)
+            D.load_state_dict(R.synth_state(R.discriminator_spec(o), 9))
+            D = D.cuda().train()
+            gp = pkg.GradientPenalty(10)(D, real.cuda(), fake.cuda(), alpha=alpha)
+            gp.backward()
+            res[on] = (float(gp.detach()), {n: p.grad.clone() for n, p in D.named_parameters() if p.grad is not None})
+        finally:
+            ops.FUSE_GP_ACCUMULATE = saved
+    assert res[True][0] == res[False][0]
+    assert len(res[False][1]) >= 20
+    for n, g in res[False][1].items():
+        close(res[True][1][n], g, 2e-5, n)
