@@ -855,12 +855,15 @@ class BatchNormActTrainBwd2(Function):
                                  gx.data_ptr(), ggamma.data_ptr(), _stream())
         fwd = ctx.link["fwd"]() if ctx.hand_over else None
         if fwd is not None and FUSE_GP_ACCUMULATE and _node_will_run(fwd):
+            global GP_HANDOVERS
+            GP_HANDOVERS += 1
             ctx.link["gx"] = gx                    # picked up by BatchNormActTrain2.backward of the same layer (see there)
             gx = None
         return gg, gx, ggamma, None, None, None, None, None
 
 
 FUSE_GP_ACCUMULATE = _os.environ.get("SPGAN_FUSE_GP_ACCUMULATE", "1") != "0"
+GP_HANDOVERS = 0          # diagnostics: gradient terms handed from a double-backward node to its layer's backward
 
 
 def _node_will_run(node):
