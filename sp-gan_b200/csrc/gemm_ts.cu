@@ -779,7 +779,12 @@ bool spgan_gemm_ts_supported(int64_t M, int N, int K, const float* A, int64_t ld
 // 1.5e-6 rms at K = 1280, the step's largest; longer K stays with gemm_tc.cu).
 bool spgan_gemm_tsk_supported(int64_t M, int N, int K, const float* A, int64_t lda) {
     static const bool on = [] { const char* e = getenv("SPGAN_TSK"); return !(e && e[0] == '0'); }();
-    return on && M >= BM && M < (1LL << 31) && N >= 16 && K > MAX_KB * BK && K <= 1536 && K % (2 * BK) == 0 && (lda % 4) == 0 &&
+    // K = 256 with at most two column tiles also runs better here: gemm_ts_kernel holds a K = 256 operand in ONE TMEM
+    // region, so with only two column tiles per row tile the conversion of the next row tile is exposed (SPGAN_TSK256=0
+    // keeps those on gemm_ts_kernel)
+    static const bool k256 = [] { const char* e = getenv("SPGAN_TSK256"); return !(e && e[0] == '0'); }();
+    const bool k_ok = (K > MAX_KB * BK && K <= 1536 && K % (2 * BK) == 0) || (k256 && K == MAX_KB * BK && N <= 2 * BN);
+    return on && M >= BM && M < (1LL << 31) && N >= 16 && k_ok && (lda % 4) == 0 &&
            (reinterpret_cast<uintptr_t>(A) & 15) == 0 && encode_tiled_fn() != nullptr;
 }
 
@@ -829,7 +834,7 @@ int spgan_gemm_ts(int transB, int64_t M, int N, int K, const float* A, int64_t l
               (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0)) ? 1 : 0;
     const int m_tiles = (int)((M + BM - 1) / BM);
     const int grid = m_tiles < kNumSMs ? m_tiles : kNumSMs;
-    if (K > MAX_KB * BK) {
+    if (K > MAX_KB * BK || (K == MAX_KB * BK && a_scale == nullptr && col_sum == nullptr && spgan_gemm_tsk_supported(M, N, K, A, lda))) {
         if (a_scale != nullptr || col_sum != nullptr || K % (2 * BK) != 0) return SPGAN_E_UNSUPPORTED;
         cudaError_t e = cudaFuncSetAttribute(gemm_tsk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
