@@ -364,7 +364,6 @@ struct NormApplyOp4 {
 struct NormBwdApplyOp4 {
     const float* g; const float* x; float slope; int C; float inv_n; const float* mean;
     const float* rstd; const float* gamma; const float* beta; const float* sg; const float* sgx; float* dx;
-    const float* addend = nullptr;        // optional [R, C]: dx = (the BatchNorm backward) + addend
     struct State { float4 mean, rstd, gamma, beta, coef, a, b; };     // dx = coef * (g' - a - xh * b)
     __device__ State init(int c4, int64_t seg) const {
         const float4 m = ld4(mean + seg * C + c4 * 4), r = ld4(rstd + seg * C + c4 * 4);
@@ -377,9 +376,22 @@ struct NormBwdApplyOp4 {
         float4 gi = ld4(g + i);
         const float4 xh = mul4(sub4(ld4(x + i), st.mean), st.rstd);
         if (slope != 1.f) gi = mask4(gi, fma4(xh, st.gamma, st.beta), slope);
-        float4 res = mul4(st.coef, sub4(sub4(gi, st.a), mul4(xh, st.b)));
-        if (addend) res = add4(res, ld4(addend + i));
-        st4(dx + i, res);
+        st4(dx + i, mul4(st.coef, sub4(sub4(gi, st.a), mul4(xh, st.b))));
+    }
+};
+// the same map with dx = (the BatchNorm backward) + addend[R, C] (its own type: the plain map's code is untouched -- a
+// runtime `if (addend)` in the shared struct cost every BatchNorm backward 40 %)
+struct NormBwdApplyAddOp4 {
+    NormBwdApplyOp4 base; const float* addend;
+    using State = NormBwdApplyOp4::State;
+    __device__ State init(int c4, int64_t seg) const { return base.init(c4, seg); }
+    __device__ void apply(const State& st, int64_t r, int c4) const {
+        const int64_t i = r * base.C + c4 * 4;
+        float4 gi = ld4(base.g + i);
+        const float4 xh = mul4(sub4(ld4(base.x + i), st.mean), st.rstd);
+        const float4 ad = ld4(addend + i);
+        if (base.slope != 1.f) gi = mask4(gi, fma4(xh, st.gamma, st.beta), base.slope);
+        st4(base.dx + i, add4(mul4(st.coef, sub4(sub4(gi, st.a), mul4(xh, st.b))), ad));
     }
 };
 struct DblBwdApplyOp4 {
@@ -1175,9 +1187,9 @@ extern "C" int spgan_norm_bwd_apply_add(const float* g, const float* x, float sl
     if (!(C % 4 == 0 && al16(g) && al16(x) && al16(dx) && al16(addend) && al16(mean) && al16(rstd) && al16(sg) && al16(sgx) &&
           (!gamma || al16(gamma)) && (!beta || al16(beta))))
         return SPGAN_E_UNSUPPORTED;
-    NormBwdApplyOp4 op{g, x, slope, C, 1.f / (float)R, mean, rstd, gamma, beta, sg, sgx, dx};
-    op.addend = addend;
-    return fastnorm::run_map(R, C, R, as_stream(s), op);
+    return fastnorm::run_map(R, C, R, as_stream(s),
+                             NormBwdApplyAddOp4{NormBwdApplyOp4{g, x, slope, C, 1.f / (float)R, mean, rstd, gamma, beta, sg, sgx, dx},
+                                                addend});
 }
 extern "C" int spgan_bn_dbl_bwd_reduce(const float* g, const float* u, const float* x, int64_t R, int C,
                                        const float* mean, float* sums, void* ws, spgan_stream_t s) {
