@@ -1283,6 +1283,15 @@ def batch_norm_act(y, bn, slope):
         else:
             z, mean, var = BatchNormActTrain.apply(y, bn.weight, bn.bias, bn.eps, slope, run)
         return z
+    if _TWICE_DIFFERENTIABLE:
+        # GradientPenalty(D.eval(), ...): frozen statistics make the layer an affine map followed by the activation;
+        # composed from the closed (twice differentiable) operator set: y = lrelu(x * (gamma rstd) + (beta - rm gamma rstd))
+        y2 = _c(_rows2d(y))
+        R, C = y2.shape
+        sc = Mul.apply(bn.weight.view(1, C), rsqrt_eps(bn.running_var, bn.eps).view(1, C))
+        sh = sub(bn.bias.view(1, C), Mul.apply(bn.running_mean.view(1, C), sc))
+        z = AddSegVec.apply(Mul.apply(y2, BcastSeg.apply(sc, R, R)), sh, R)
+        return LRelu.apply(z, slope) if slope != 1.0 else z
     return NormAffineEval.apply(y, bn.weight, bn.bias, bn.running_mean, rsqrt_eps(bn.running_var, bn.eps), slope)
 
 

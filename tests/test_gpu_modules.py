@@ -142,6 +142,47 @@ def test_gradient_penalty_double_backward():
     _check_bufs(D, g)
 
 
+def test_gradient_penalty_on_an_eval_mode_critic():
+    """GradientPenalty(D.eval(), ...) (frozen BatchNorm statistics): the reference supports it through plain autograd;
+    here the eval-mode BatchNorm under the double backward is composed from the twice-differentiable operator set.
+    Checked against the live oracle (torch CPU), value and every parameter gradient."""
+    pkg = _pkg()
+    o = R.default_opts(np=256)
+    spec = R.discriminator_spec(o)
+    state = R.synth_state(spec, 33)
+    for k in state:                                              # non-trivial running statistics
+        if k.endswith("running_mean"):
+            state[k] = 0.1 * torch.randn_like(state[k])
+        if k.endswith("running_var"):
+            state[k] = 0.5 + torch.rand_like(state[k])
+    D = pkg.Discriminator(o)
+    D.load_state_dict(state)
+    D = D.cuda().eval()
+    rng = np.random.default_rng(5)
+    real = torch.from_numpy((0.5 * rng.standard_normal((2, 3, 256))).astype(np.float32))
+    fake = torch.from_numpy((0.5 * rng.standard_normal((2, 3, 256))).astype(np.float32))
+    alpha = torch.rand(2, 1, 1, generator=torch.Generator().manual_seed(1))
+    gp = pkg.GradientPenalty(10)(D, real.cuda(), fake.cuda(), alpha=alpha)
+    gp.backward()
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in state.items()}
+    gp_ref = R.gradient_penalty(lambda t: R.discriminator_forward(sd, t, False), real, fake, alpha)
+    gp_ref.backward()
+    assert abs(float(gp) - float(gp_ref)) <= TOL * abs(float(gp_ref)), (float(gp), float(gp_ref))
+    scale = max(float(v.grad.abs().max()) for v in sd.values() if v.requires_grad and v.grad is not None)
+    n = 0
+    for name, p in D.named_parameters():
+        ref = sd[name].grad
+        if ref is None or p.grad is None:
+            continue
+        err = float((p.grad.cpu() - ref.reshape(p.grad.shape)).abs().max())
+        assert err <= TOL * max(float(ref.abs().max()), 1e-2 * scale), (name, err)
+        n += 1
+    assert n >= 10
+    for name, b in D.named_buffers():                            # eval mode: the buffers do not move
+        assert torch.equal(b.cpu(), state[name]), name
+
+
 @pytest.mark.parametrize("tag,kw", [("default", {}), ("off_znorm", {"off": True, "z_norm": True}),
                                     ("use_head", {"use_head": True}), ("eql_attn", {"eql": True, "attn": True})])
 def test_generator(tag, kw, sphere256):
