@@ -276,7 +276,9 @@ int launch_simt(int transA, int transB, int64_t M, int N, int64_t K, const float
 int spgan_gemm_simt(int transA, int transB, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int accumulate, cudaStream_t st,
                     void* workspace, size_t workspace_bytes) {
-    if (N <= 64)
+    // narrow tiles also when 128-wide ones would leave most SMs idle (the M = 64 heads and their weight gradients:
+    // 32 CTAs of 128 x 128 -> 64 of 128 x 64); the k order of every output's FMA chain does not depend on the tile width
+    if (N <= 64 || ceil_div64(M, BM) * ((N + 127) / 128) < kNumSMs / 2)
         return launch_simt<64>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st, workspace,
                                workspace_bytes);
     return launch_simt<128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, accumulate, st, workspace,
