@@ -374,6 +374,8 @@ def run_gpu(args, real_stdout):
                 a[2] += gemm_flops(ia)
             elif name == "spgan_gemm_fused":                         # (transB, M, N, K, ...)
                 a[2] += 2.0 * ia[1] * ia[2] * ia[3]
+            elif name == "spgan_gemm_wgrad_fused":                   # (Mo, No, K, ...)
+                a[2] += 2.0 * ia[0] * ia[1] * ia[2]
         total = sum(a[0] for a in agg.values())
         if os.environ.get("SPGAN_BENCH_GEMM_TABLE") == "1":        # diagnostic: GEMM time by shape (stderr)
             byshape = {}
@@ -491,11 +493,12 @@ def run_gpu(args, real_stdout):
                         "tensor_pipe_active_pct_ncu": cap.get("tensor_pipe_pct"),
                         "note": note, "peak_source": peak_src, "mma_per_product": 3,
                         "frac_of_attainable": ach / (peak_tf() / (3.0 if eng == 3 else 6.0))}
-        g, gf = agg.get("spgan_gemm"), agg.get("spgan_gemm_fused")
+        g, gf, gw = agg.get("spgan_gemm"), agg.get("spgan_gemm_fused"), agg.get("spgan_gemm_wgrad_fused")
         if g or gf:
-            g = [sum(x) for x in zip(g or [0.0, 0, 0.0], gf or [0.0, 0, 0.0])]
+            g = [sum(x) for x in zip(g or [0.0, 0, 0.0], gf or [0.0, 0, 0.0], gw or [0.0, 0, 0.0])]
             ach = g[2] / (g[0] / 1e3) / 1e12
-            roofline_all = {"kernel": "spgan_gemm + spgan_gemm_fused, all %d launches of the step" % g[1], "bound": "tensor",
+            roofline_all = {"kernel": "spgan_gemm + spgan_gemm_fused + spgan_gemm_wgrad_fused, all %d launches of the step "
+                                      "(tensor-core and CUDA-core routes alike)" % g[1], "bound": "tensor",
                             "achieved": ach, "peak": peak_tf(), "unit": "TFLOP/s", "frac": ach / peak_tf(),
                             "share_of_step": g[0] / total}
             if roofline is None:
