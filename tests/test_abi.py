@@ -53,3 +53,29 @@ def test_no_oracle_or_fallback_in_product():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/spgan_b200.h compiles as C99 (no C++ or torch types in the signatures) and a
+    C translation unit links against the library (symbols resolved by name, nothing mangled)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use.c"
+    src.write_text('#include "spgan_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    size_t ws = spgan_gemm_workspace(3, 128, 64);\n'
+                   '    printf("%d %s %zu\\n", spgan_abi_version(), spgan_error_string(-2), ws);\n'
+                   '    return spgan_abi_version() == 1 ? 0 : 1;\n}\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    m = _lib_mod()
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(m.LIB_PATH)
+    rc = subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:libspgan_b200.so",
+                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert rc.returncode == 0, rc.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("1 "), (out.stdout, out.stderr)
